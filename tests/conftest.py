@@ -1,0 +1,38 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box via gpurun)')
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz'))
+
+
+def load_golden(name):
+    """Returns (fixture dict, (u, W, y)) with inputs regenerated from the stored seed."""
+    from oracle import routing_np as onp
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + '.npz')))
+    B, N, C, K, D, R, seed = [int(x) for x in g['dims']]
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=seed)
+    chk = np.array([u.astype(np.float64).sum(), W.astype(np.float64).sum(), float(y.sum())])
+    assert np.allclose(chk, g['in_checksum'], rtol=0, atol=1e-9), 'input RNG drifted from the fixture'
+    g['R'] = R
+    return g, (u, W, y)
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  -- the 'rel' the north_star tolerance is quoted in."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

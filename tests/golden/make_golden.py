@@ -1,0 +1,132 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference's `models.py` / `loss_fns.py` are imported as they are; the only shim is a stub for
+`matplotlib.colors` (not installed here; used only by `utils.augmentation`, which the training
+loop has commented out, reference main.py:56).  Inputs come from
+`oracle.routing_np.make_inputs(seed)` so that tests can regenerate them bit-identically on any
+box; each fixture stores an input checksum to detect RNG drift.
+
+Per case the fixture holds what the reference layer + its own loss + autograd produced in fp32
+(and in fp64, as the tie-breaker for tolerance budgeting):
+  v [B,C,D], c_last [B,N,C] (last-iteration softmax, captured by wrapping F.softmax),
+  loss (capsule_loss with recon off), du [B,N,K], dW [N,C,K,D]  (or a strided probe of dW for
+  the full-size case, to keep the fixture small).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+
+# name: (B, N, C, K, D, R, seed, full_dW)
+CASES = {
+    'caps_c43_d16_r3':   (4, 12, 43, 8, 16, 3, 11, True),    # CapsuleNet head, shrunk in N
+    'caps_c10_d16_r3':   (7, 40, 10, 8, 16, 3, 12, True),
+    'caps_c43_d16_r1':   (3, 8, 43, 8, 16, 1, 13, True),    # single iteration (no agreement step)
+    'caps_c43_d16_r5':   (3, 8, 43, 8, 16, 5, 14, True),
+    'dark_c1_d5_r3':     (9, 512, 1, 8, 5, 3, 15, True),     # DarkCapsuleNet head (models.py:368-370)
+    'dark3_c43_d21_r3':  (2, 6, 43, 8, 21, 3, 16, True),    # DarkCapsuleNet3 head shape (models.py:431-433)
+    'dark2_c49_d48_r3':  (2, 4, 49, 8, 48, 3, 17, True),     # DarkCapsuleNet2 head shape (models.py:327-329)
+    'sweep_c43_d32_r2':  (5, 6, 43, 8, 32, 2, 18, True),
+    'caps_b1':           (1, 8, 43, 8, 16, 3, 19, True),    # batch of one
+    'caps_full_n1296':   (2, 1296, 43, 8, 16, 3, 20, False), # the real CapsuleNet routing shape
+    'caps_full_n1152':   (3, 1152, 43, 8, 16, 3, 21, False), # BASELINE.json config 2 shape
+}
+PROBE_STRIDE = 997
+
+
+def import_reference():
+    mpl = types.ModuleType('matplotlib')
+    col = types.ModuleType('matplotlib.colors')
+    col.rgb_to_hsv = lambda a: a
+    col.hsv_to_rgb = lambda a: a
+    mpl.colors = col
+    sys.modules.setdefault('matplotlib', mpl)
+    sys.modules.setdefault('matplotlib.colors', col)
+    sys.path.insert(0, REF)
+    import models as ref_models      # noqa: E402
+    import loss_fns as ref_loss      # noqa: E402
+    return ref_models, ref_loss
+
+
+class P:  # stand-in for utils.Params (an attribute bag, reference utils.py:14-31)
+    device = 'cpu'
+    recon = False
+    recon_coef = 5e-4
+
+
+def run_reference(ref_models, ref_loss, u, W, y, R, dtype):
+    B, N, K = u.shape
+    _, C, _, D = W.shape
+    params = P()
+    params.n_classes = C
+    layer = ref_models.CapsuleLayer(params, n_caps=C, n_nodes=N, in_C=K, out_C=D, n_iter=R)
+    with torch.no_grad():
+        layer.route_weights.copy_(torch.from_numpy(W)[None])
+    layer = layer.to(dtype)
+    ut = torch.from_numpy(u).to(dtype).requires_grad_(True)
+
+    captured = []
+    real_softmax = ref_models.F.softmax
+
+    def spy(x, dim):
+        out = real_softmax(x, dim=dim)
+        captured.append(out)
+        return out
+    ref_models.F.softmax = spy
+    try:
+        out = layer(ut)                                    # [B,1,C,1,D]
+    finally:
+        ref_models.F.softmax = real_softmax
+    v = out.reshape(B, C, D)
+    scores = (v ** 2).sum(dim=-1) ** 0.5                   # reference models.py:117
+    loss = ref_loss.capsule_loss(scores, torch.from_numpy(y), params)
+    loss.backward()
+    c_last = captured[-1][:, :, :, 0, 0]
+    return dict(v=v.detach().numpy(), c=c_last.detach().numpy(), loss=float(loss.detach()),
+                du=ut.grad.numpy(), dW=layer.route_weights.grad[0].numpy())
+
+
+def main():
+    from oracle import routing_np as onp
+    ref_models, ref_loss = import_reference()
+    torch.manual_seed(0)
+    torch.set_num_threads(1)   # one thread: reduction order (hence the fp32 bits) is reproducible
+    for name, (B, N, C, K, D, R, seed, full) in CASES.items():
+        u, W, y = onp.make_inputs(B, N, C, K, D, seed=seed)
+        r32 = run_reference(ref_models, ref_loss, u, W, y, R, torch.float32)
+        r64 = run_reference(ref_models, ref_loss, u, W, y, R, torch.float64)
+        blob = dict(dims=np.array([B, N, C, K, D, R, seed], dtype=np.int64),
+                    in_checksum=np.array([u.astype(np.float64).sum(), W.astype(np.float64).sum(),
+                                          float(y.sum())]),
+                    v=r32['v'], loss=np.float32(r32['loss']), du=r32['du'],
+                    v64=r64['v'], loss64=np.float64(r64['loss']), du64=r64['du'])
+        if full:
+            blob.update(c=r32['c'], dW=r32['dW'], c64=r64['c'].astype(np.float64),
+                        dW64_probe=r64['dW'].reshape(-1)[::7].copy(), probe_stride=np.int64(7))
+        else:
+            blob.update(c_probe=r32['c'].reshape(-1)[::PROBE_STRIDE].copy(),
+                        c64_probe=r64['c'].reshape(-1)[::PROBE_STRIDE].copy(),
+                        dW_probe=r32['dW'].reshape(-1)[::PROBE_STRIDE].copy(),
+                        dW64_probe=r64['dW'].reshape(-1)[::PROBE_STRIDE].copy(),
+                        dW64_sum=np.float64(r64['dW'].sum()),
+                        dW64_abs_sum=np.float64(np.abs(r64['dW']).sum()),
+                        probe_stride=np.int64(PROBE_STRIDE))
+        path = os.path.join(HERE, name + '.npz')
+        np.savez_compressed(path, **blob)
+        print('%-20s B=%d N=%d C=%d K=%d D=%d R=%d loss=%.6f -> %s (%d KB)' % (
+            name, B, N, C, K, D, R, r32['loss'], os.path.basename(path), os.path.getsize(path) // 1024))
+
+
+if __name__ == '__main__':
+    main()
