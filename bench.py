@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- capsule-routing samples/sec, fwd+bwd, on N B200s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+
+A "step" is one pass of the hot path over one batch of synthetic input: routing forward
+(reference models.py:70-79), margin loss (loss_fns.py:12-17,23), backward to du and dW
+(autograd of the same), on BASELINE.json configs[1]: 1152 primary capsules (8D) -> 43 class
+capsules (16D), 3 routing iterations.  Per-GPU batch is fixed (weak scaling); ranks shard the
+batch with no data-path collective and average dW with one NCCL all-reduce per step.
+
+Prints ONE JSON line (rank 0).  `value` times K steps with inputs resident in HBM (CUDA events,
+max over ranks); `e2e` times the same K steps through the host-buffer C-ABI call
+(caps_route_step_host: H2D of u,y from pinned memory and D2H of the loss inside the timed region);
+`roofline` is for the dominant kernel (the pass kernel) from CUDA events recorded around every
+launch in the timed region; `cpu_baseline` is the oracle's op-for-op torch port of the reference
+path on this box's host cores over a bounded sample.  `--impl reference` times only that CPU path.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES, N_CAPS, IN_C, OUT_C, N_ITER = 1152, 43, 8, 16, 3
+METRIC = 'capsule-routing samples/sec fwd+bwd'
+UNIT = 'samples/s'
+KCLASS = ['layout', 'pass_A0', 'pass_L', 'pass_A', 'squash', 'softmax', 'grad', 'du_reduce', 'loss', 'other']
+
+
+def workload_name(batch):
+    return 'configs[1]: routing layer alone, %d primary caps (8D) -> %d class caps (16D), %d iters, batch %d per GPU' % (
+        N_NODES, N_CAPS, N_ITER, batch)
+
+
+def flops_per_sample(N=N_NODES, C=N_CAPS, K=IN_C, D=OUT_C, R=N_ITER):
+    """Algorithmic fwd+bwd flops: 6 NCKD + (6R-4) 2 NCD."""
+    return 6.0 * N * C * K * D + (6 * R - 4) * 2.0 * N * C * D
+
+
+def hbm_bytes_per_step(B, N=N_NODES, C=N_CAPS, K=IN_C, D=OUT_C, R=N_ITER):
+    """Algorithmic HBM bytes: (12 NK + (8+8R) CD) per sample + 12 NCKD per batch."""
+    return B * (12.0 * N * K + (8 + 8 * R) * C * D) + 12.0 * N * C * K * D
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 <= ts <= t1 + 0.2:
+                sm.append(clk)
+                for name, val in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        if not sm:
+            sm = [float(l.split(',')[1]) for _, l in self.lines[-3:] if len(l.split(',')) > 2] or [0.0]
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the ONLY places bench.py touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(sample):
+    import numpy as np
+    import torch
+    from oracle import routing_np as onp
+    from oracle import routing_torch as ot
+    torch.set_num_threads(os.cpu_count() or 1)
+    u, W, y = onp.make_inputs(sample, N_NODES, N_CAPS, IN_C, OUT_C, seed=0)
+    ut, Wt, yt = torch.from_numpy(u), torch.from_numpy(W)[None], torch.from_numpy(y)
+
+    def step():
+        return ot.routing_step_t(ut, Wt, yt, N_ITER)
+    return step, torch.get_num_threads()
+
+
+def run_cpu_baseline(sample=64, reps=2):
+    """Times the torch op-for-op port of the reference path (oracle/routing_torch.py) on the host."""
+    step, threads = cpu_reference_step_fn(sample)
+    step()                                   # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {'value': sample / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': '%d steps of a %d-sample micro-batch of the same workload (reference needs ~65 MB/sample; '
+                      'its samples/s is flat in batch)' % (reps, sample),
+            'ms_per_microbatch': dt * 1e3}
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    sample = args.cpu_sample
+    step, threads = cpu_reference_step_fn(sample)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args.batch),
+                   'note': 'reference CPU path (torch op-for-op port in oracle/routing_torch.py; the Python '
+                           'reference cannot travel to the GPU box); each step is a %d-sample micro-batch' % sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                         'sample': '%d-sample micro-batch per step' % sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def main_gpu(args, rank, world, device):
+    import torch
+    import torch.distributed as dist
+    import cs231_capsule_yolo_traffic_sign_detection_b200 as pkg
+    from cs231_capsule_yolo_traffic_sign_detection_b200 import _cabi
+    L = _cabi.lib()                       # raises if the CUDA library is missing (no fallback)
+    B, N, C, K, D, R = args.batch, N_NODES, N_CAPS, IN_C, OUT_C, N_ITER
+    if args.spt:
+        _cabi.set_tuning('spt', args.spt)
+    if args.isplit:
+        _cabi.set_tuning('isplit', args.isplit)
+    torch.manual_seed(1234 + rank)
+    g = torch.Generator(device='cpu').manual_seed(1234 + rank)
+
+    # synthetic inputs of the reference's shape/value range: u = squash(N(0,1)), W = 0.1 N(0,1)
+    x = torch.randn(B, N, K, generator=g)
+    sq = (x ** 2).sum(-1, keepdim=True)
+    u_host = ((sq / (1 + sq)) * x / sq.sqrt()).contiguous().pin_memory()
+    y_host = torch.randint(0, C, (B,), generator=g).pin_memory()
+    gw = torch.Generator(device='cpu').manual_seed(99)           # same weights on every rank
+    W = (0.1 * torch.randn(N, C, K, D, generator=gw)).to(device)
+    u = u_host.to(device)
+    y = y_host.to(device)
+    v = torch.empty(B, C, D, device=device)
+    du = torch.empty(B, N, K, device=device)
+    dW = torch.empty_like(W)
+    loss = torch.empty((), device=device)
+    nbytes = L.caps_route_workspace_bytes(B, N, C, K, D, R, 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+    P = lambda t: t.data_ptr()
+
+    def step_device():
+        _cabi.check(L.caps_route_forward(P(u), P(W), P(v), None, P(ws), nbytes, B, N, C, K, D, R, 1, stream), 'fwd')
+        _cabi.check(L.caps_margin_loss(P(v), P(y), 1.0 / B, P(loss), None, B, C, D, stream), 'loss')
+        _cabi.check(L.caps_route_backward(P(u), P(W), None, P(y), 1.0 / B, None, P(du), P(dW), P(ws), nbytes,
+                                          B, N, C, K, D, R, stream), 'bwd')
+        if world > 1:
+            dist.all_reduce(dW)            # data-parallel gradient average (sum here; scale folded into lr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t1 = time.time()
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, t0, t1
+
+    # ---- kernel-resident throughput -----------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(device.index if device.index is not None else 0)
+    clocks.start()
+    time.sleep(0.25)
+    _cabi.set_tuning('profile', 1)
+    launches0 = L.caps_kernel_launch_count()
+    ms, t0, t1 = timed(step_device, args.steps)
+    launches = L.caps_kernel_launch_count() - launches0
+    ms_cls = (ctypes.c_double * len(KCLASS))()
+    n_cls = (ctypes.c_long * len(KCLASS))()
+    _cabi.check(L.caps_profile_collect(ms_cls, n_cls, len(KCLASS)), 'profile')
+    _cabi.set_tuning('profile', 0)
+    clk = clocks.stop(t0, t1)
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    loss_val = float(loss)
+
+    # ---- end to end through the host-buffer C-ABI call ----------------------------------------
+    host = pkg.HostStep(B, N, C, K, D, R, device=device)
+
+    def step_host():
+        host(u_host, y_host, W, dW)
+        if world > 1:
+            dist.all_reduce(dW)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_host()
+    ms_e2e, _, _ = timed(step_host, args.steps)
+    e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
+
+    if rank != 0:
+        return 0
+
+    # ---- rooflines --------------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    hbm_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    fma_ms, fma_fl = ctypes.c_float(), ctypes.c_double()
+    _cabi.check(L.caps_fma_peak(20000, ctypes.byref(fma_ms), ctypes.byref(fma_fl), stream), 'fma_peak')
+    fma_peak = fma_fl.value / (fma_ms.value * 1e-3) / 1e12
+
+    per_class = {KCLASS[i]: {'ms_per_step': ms_cls[i] / args.steps, 'launches_per_step': n_cls[i] / args.steps}
+                 for i in range(len(KCLASS)) if n_cls[i]}
+    n_pass = sum(n_cls[i] for i in (1, 2, 3))
+    ms_pass = sum(ms_cls[i] for i in (1, 2, 3))
+    avg_pass_ms = ms_pass / max(n_pass, 1)
+    # algorithmic work of ONE pass-kernel launch: the K=8 contraction + one [D] dot/axpy per (b,i,j);
+    # bytes: u read + the [B,N,C] coefficient array read or written + W read once.
+    pass_flops = B * (2.0 * N * C * K * D + 2.0 * N * C * D)
+    pass_bytes = B * (4.0 * N * K + 4.0 * N * C) + 4.0 * N * C * K * D
+    ach_gbs = pass_bytes / (avg_pass_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'k_pass (u_hat recompute sweep; %d launches/step)' % (n_pass // args.steps),
+                'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
+                'traffic': None, 'peak_source': hbm_src,
+                'note': 'this kernel is fp32-FMA bound, not HBM bound (SURVEY 8d): see roofline_fp32'}
+    ach_tf = pass_flops / (avg_pass_ms * 1e-3) / 1e12
+    roofline_fp32 = {'bound': 'fp32_fma', 'kernel': 'k_pass', 'achieved': ach_tf, 'peak': fma_peak, 'unit': 'TFLOP/s',
+                     'frac': ach_tf / fma_peak, 'peak_source': 'measured live: caps_fma_peak (register-operand FFMA chains)',
+                     'share_of_step': ms_pass / ms}
+    step_tf = flops_per_sample() * B / (ms_per_step * 1e-3) / 1e12
+    step_gbs = hbm_bytes_per_step(B) / (ms_per_step * 1e-3) / 1e9
+    roofline_step = {'algorithmic_tflops': step_tf, 'frac_of_fp32_peak': step_tf / fma_peak,
+                     'algorithmic_gbs': step_gbs, 'frac_of_hbm_peak': step_gbs / hbm_peak}
+
+    cpu = run_cpu_baseline(args.cpu_sample, 2) if not args.no_cpu else None
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(B), 'n_nodes': N, 'n_caps': C, 'in_C': K, 'out_C': D, 'n_iter': R,
+                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                   'l2': 'inputs larger than L2 (u = %.0f MB per step; saved coupling arrays %.1f GB)' % (
+                       B * N * K * 4 / 1e6, 4.0 * B * N * C * 4 / 1e9),
+                   'loss': loss_val},
+        'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes,
+                'd2h_bytes_per_step': host.d2h_bytes, 'ms_per_step': ms_e2e / args.steps,
+                'api': 'caps_route_step_host (pinned host u,y -> device; loss -> host)'},
+        'gpu_launches': int(launches),
+        'clocks': clk,
+        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'roofline_step': roofline_step,
+        'kernel_ms_per_step': per_class,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=8192, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--cpu-sample', type=int, default=64, help='micro-batch of the CPU baseline')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--spt', type=int, default=0)
+    ap.add_argument('--isplit', type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        return main_reference(args, rank, world)
+    from cs231_capsule_yolo_traffic_sign_detection_b200.parallel import init_from_env
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+    rank, world, device = init_from_env()
+    try:
+        return main_gpu(args, rank, world, device)
+    finally:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,15 @@
+"""B200-native capsule dynamic routing (the hot path of
+Cranial-XIX/cs231-capsule-yolo-traffic-sign-detection), behind the reference's module interface.
+
+    from cs231_capsule_yolo_traffic_sign_detection_b200 import CapsuleLayer
+    import models; models.CapsuleLayer = CapsuleLayer      # then build CapsuleNet / DarkCapsuleNet
+
+The arithmetic lives in libcaps_routing.so (hand-written sm_100a CUDA, C ABI in
+include/caps_routing.h).  Importing the package does not need a GPU; running the routing branch
+does, and fails loudly without the built library -- there is no CPU fallback."""
+from . import _cabi
+from .capsule import (CapsuleLayer, HostStep, dynamic_routing, routing_margin_loss)
+from .parallel import GradBucket, init_from_env, shard_bounds
+
+__all__ = ['CapsuleLayer', 'HostStep', 'dynamic_routing', 'routing_margin_loss',
+           'GradBucket', 'init_from_env', 'shard_bounds', '_cabi']

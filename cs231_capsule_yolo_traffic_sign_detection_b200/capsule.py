@@ -1,0 +1,237 @@
+"""Host-side mirror of the reference's capsule layer, over the C ABI in include/caps_routing.h.
+
+`CapsuleLayer` keeps the reference's constructor, attributes, parameter names/shapes and output
+shape (reference models.py:46-83), so it drops into `models.CapsuleNet` / `models.DarkCapsuleNet`
+(assign `models.CapsuleLayer = CapsuleLayer` before building the model) with `main.py`,
+`loss_fns.py`, `predict_fns.py` unchanged.  The caps->caps branch runs in the hand-written
+sm_100a kernels; the conv->caps branch (n_nodes == -1) stays stock PyTorch (its squash uses the
+CUDA squash kernel when the input is a CUDA fp32 tensor).
+
+PyTorch is plumbing here (device memory, streams, autograd graph); the arithmetic is in
+libcaps_routing.so.  There is no CPU fallback: CPU tensors on the routing branch raise.
+"""
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_routing_inputs(u, W5):
+    if not (u.is_cuda and W5.is_cuda):
+        raise RuntimeError('capsule routing runs on a CUDA device only (no CPU fallback): '
+                           'got u on %s, route_weights on %s' % (u.device, W5.device))
+    if u.dtype != torch.float32 or W5.dtype != torch.float32:
+        raise RuntimeError('capsule routing is fp32 only: got %s / %s' % (u.dtype, W5.dtype))
+    if u.dim() != 3 or W5.dim() != 5 or W5.shape[0] != 1:
+        raise RuntimeError('expected u [B,N,K] and route_weights [1,N,C,K,D], got %s and %s'
+                           % (tuple(u.shape), tuple(W5.shape)))
+    if u.shape[1] != W5.shape[1] or u.shape[2] != W5.shape[3]:
+        raise RuntimeError('shape mismatch: u %s vs route_weights %s' % (tuple(u.shape), tuple(W5.shape)))
+
+
+def _forward_impl(u, W5, n_iter, with_grad, want_c):
+    L = _cabi.lib()
+    B, N, K = u.shape
+    _, _, C, _, D = W5.shape
+    u = u.contiguous()
+    W = W5.contiguous()
+    v = torch.empty((B, C, D), device=u.device, dtype=torch.float32)
+    c = torch.empty((B, N, C), device=u.device, dtype=torch.float32) if want_c else None
+    nbytes = L.caps_route_workspace_bytes(B, N, C, K, D, n_iter, int(with_grad))
+    if nbytes == 0:
+        raise RuntimeError('capsule routing: unsupported dims B=%d N=%d C=%d K=%d D=%d n_iter=%d '
+                           '(K must be 8, D <= 48, n_iter <= 5)' % (B, N, C, K, D, n_iter))
+    ws = torch.empty((nbytes,), device=u.device, dtype=torch.uint8)
+    with torch.cuda.device(u.device):
+        _cabi.check(L.caps_route_forward(_ptr(u), _ptr(W), _ptr(v), _ptr(c), _ptr(ws), nbytes,
+                                         B, N, C, K, D, n_iter, int(with_grad), _stream()),
+                    'caps_route_forward')
+    return u, W, v, c, ws
+
+
+def _backward_impl(u, W, ws, grad_v, y, margin_scale, loss_grad, n_iter, need_du):
+    L = _cabi.lib()
+    B, N, K = u.shape
+    _, _, C, _, D = W.shape
+    dW = torch.empty_like(W)
+    du = torch.empty_like(u) if need_du else None
+    if grad_v is not None:
+        grad_v = grad_v.contiguous()
+    with torch.cuda.device(u.device):
+        _cabi.check(L.caps_route_backward(_ptr(u), _ptr(W), _ptr(grad_v), _ptr(y), float(margin_scale),
+                                          _ptr(loss_grad), _ptr(du), _ptr(dW), _ptr(ws), ws.numel(),
+                                          B, N, C, K, D, n_iter, _stream()),
+                    'caps_route_backward')
+    return du, dW
+
+
+class _RoutingFn(torch.autograd.Function):
+    """v = routing(u, W): autograd node over caps_route_forward / caps_route_backward."""
+
+    @staticmethod
+    def forward(ctx, u, W5, n_iter, want_c):
+        _check_routing_inputs(u, W5)
+        ctx.set_materialize_grads(False)
+        with_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        u_c, W_c, v, c, ws = _forward_impl(u, W5, n_iter, with_grad, want_c)
+        if with_grad:
+            ctx.save_for_backward(u_c, W_c)
+            ctx.ws = ws
+            ctx.n_iter = n_iter
+        if want_c:
+            ctx.mark_non_differentiable(c)
+            return v, c
+        return v
+
+    @staticmethod
+    def backward(ctx, grad_v, *unused):
+        u, W = ctx.saved_tensors
+        du, dW = _backward_impl(u, W, ctx.ws, grad_v, None, 0.0, None, ctx.n_iter, ctx.needs_input_grad[0])
+        return du, (dW if ctx.needs_input_grad[1] else None), None, None
+
+
+class _RoutingMarginLossFn(torch.autograd.Function):
+    """(v, loss) = routing + margin loss; the backward kernel adds the margin-loss gradient itself
+    (reference loss_fns.py:12-17,23 on scores = |v|, models.py:117), so only the EXTRA gradient
+    flowing into v (decoder / coordinate losses) comes in through autograd."""
+
+    @staticmethod
+    def forward(ctx, u, W5, y, n_iter):
+        _check_routing_inputs(u, W5)
+        ctx.set_materialize_grads(False)
+        L = _cabi.lib()
+        with_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        u_c, W_c, v, _, ws = _forward_impl(u, W5, n_iter, with_grad, False)
+        B, C, D = v.shape
+        y = y.to(device=u.device, dtype=torch.int64).contiguous()
+        loss = torch.empty((), device=u.device, dtype=torch.float32)
+        with torch.cuda.device(u.device):
+            _cabi.check(L.caps_margin_loss(_ptr(v), _ptr(y), 1.0 / B, _ptr(loss), None, B, C, D, _stream()),
+                        'caps_margin_loss')
+        if with_grad:
+            ctx.save_for_backward(u_c, W_c, y)
+            ctx.ws = ws
+            ctx.n_iter = n_iter
+        return v, loss
+
+    @staticmethod
+    def backward(ctx, grad_v, grad_loss):
+        u, W, y = ctx.saved_tensors
+        B = u.shape[0]
+        if grad_loss is None:
+            y_arg, lg = None, None
+        else:
+            y_arg, lg = y, grad_loss.to(torch.float32).contiguous()
+        du, dW = _backward_impl(u, W, ctx.ws, grad_v, y_arg, 1.0 / B, lg, ctx.n_iter, ctx.needs_input_grad[0])
+        return du, (dW if ctx.needs_input_grad[1] else None), None, None
+
+
+class _SquashFn(torch.autograd.Function):
+    """squash over the last dim (reference models.py:64-67) through caps_squash."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L = _cabi.lib()
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        D = xc.shape[-1]
+        rows = xc.numel() // D
+        with torch.cuda.device(x.device):
+            _cabi.check(L.caps_squash(_ptr(xc), _ptr(y), rows, D, _stream()), 'caps_squash')
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xc,) = ctx.saved_tensors
+        L = _cabi.lib()
+        gy = gy.contiguous()
+        gx = torch.empty_like(xc)
+        D = xc.shape[-1]
+        with torch.cuda.device(xc.device):
+            _cabi.check(L.caps_squash_backward(_ptr(xc), _ptr(gy), _ptr(gx), xc.numel() // D, D, _stream()),
+                        'caps_squash_backward')
+        return gx
+
+
+def dynamic_routing(u, route_weights, n_iter=3, return_couplings=False):
+    """u [B,N,K], route_weights [1,N,C,K,D]  ->  v [B,C,D] (and the last couplings c [B,N,C])."""
+    return _RoutingFn.apply(u, route_weights, int(n_iter), bool(return_couplings))
+
+
+def routing_margin_loss(u, route_weights, y, n_iter=3):
+    """Fused path: returns (v [B,C,D], margin loss) with the margin-loss gradient computed inside the
+    routing backward kernel.  loss == reference capsule_loss(|v|, y) with recon off."""
+    return _RoutingMarginLossFn.apply(u, route_weights, y, int(n_iter))
+
+
+class CapsuleLayer(nn.Module):
+    """Drop-in for reference models.CapsuleLayer (models.py:46-83): same signature, attributes,
+    parameter names and shapes, same seeded initialisation draw, same output shapes."""
+
+    def __init__(self, params, n_caps, n_nodes, in_C, out_C, kernel=None, stride=None, n_iter=3):
+        super(CapsuleLayer, self).__init__()
+        self.params = params
+        self.n_iter = n_iter
+        self.n_nodes = n_nodes
+        self.n_caps = n_caps
+        if n_nodes != -1:   # caps -> caps: the routing branch (models.py:56-58)
+            self.route_weights = nn.Parameter(0.1 * torch.randn(1, n_nodes, n_caps, in_C, out_C))
+        else:               # conv -> caps: primary capsules (models.py:59-62), stock PyTorch
+            self.capsules = nn.ModuleList(
+                [nn.Conv2d(in_C, out_C, kernel, stride=stride) for _ in range(n_caps)])
+
+    def squash(self, v):
+        if v.is_cuda and v.dtype == torch.float32:
+            return _SquashFn.apply(v)
+        sq = (v ** 2).sum(dim=-1, keepdim=True)
+        return (sq / (1 + sq)) * v / torch.sqrt(sq)
+
+    def forward(self, x):
+        if self.n_nodes != -1:
+            v = dynamic_routing(x, self.route_weights, self.n_iter)       # [B,C,D]
+            B, C, D = v.shape
+            return v.view(B, 1, C, 1, D)                                   # reference output shape
+        outs = [cap(x).view(x.size(0), -1, 1) for cap in self.capsules]
+        return self.squash(torch.cat(outs, dim=-1))
+
+    def forward_margin_loss(self, x, y):
+        """Fused variant: ([B,1,C,1,D] output, margin loss); see routing_margin_loss."""
+        v, loss = routing_margin_loss(x, self.route_weights, y, self.n_iter)
+        B, C, D = v.shape
+        return v.view(B, 1, C, 1, D), loss
+
+
+class HostStep:
+    """End-to-end call with HOST buffers through caps_route_step_host: u, y come from (pinned)
+    host memory every step, the loss (and optionally v / du) go back to the host; W and dW stay
+    on the device like the reference's parameters do."""
+
+    def __init__(self, B, N, C, K, D, n_iter, device='cuda'):
+        L = _cabi.lib()
+        self.dims = (B, N, C, K, D, n_iter)
+        nbytes = L.caps_route_step_host_scratch_bytes(B, N, C, K, D, n_iter)
+        if nbytes == 0:
+            raise RuntimeError('unsupported dims %s' % (self.dims,))
+        self.device = torch.device(device)
+        self.scratch = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
+        self.loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = B * N * K * 4 + B * 8
+        self.d2h_bytes = 4
+
+    def __call__(self, u_host, y_host, W_dev, dW_dev, v_host=None, du_host=None):
+        B, N, C, K, D, R = self.dims
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().caps_route_step_host(
+                _ptr(u_host), _ptr(y_host), _ptr(W_dev), _ptr(self.loss_host), _ptr(v_host), _ptr(du_host),
+                _ptr(dW_dev), _ptr(self.scratch), self.scratch.numel(), B, N, C, K, D, R, _stream()),
+                'caps_route_step_host')
+        return self.loss_host

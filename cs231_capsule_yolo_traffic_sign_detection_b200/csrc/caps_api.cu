@@ -1,0 +1,422 @@
+// caps_routing.cu -- C ABI (include/caps_routing.h) over the sm_100a kernels in caps_kernels.cuh.
+//
+// Host-side orchestration of the routing forward (reference models.py:70-79) and its backward:
+//   forward :  prep(u) ; A0 ; squash ; { L ; softmax ; A ; squash } x (R-1)
+//   backward:  dsquash(top, +margin grad) ; { L ; softmax_bwd ; A ; dsquash } x (R-1) ; grad ; reduce(du)
+// Everything is enqueued on the caller's stream; no host synchronisation, no allocation (the
+// caller's workspace is carved deterministically from the dims).
+#include "caps_internal.h"
+
+#include <atomic>
+
+namespace caps {
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+}  // namespace caps
+
+namespace {
+
+using namespace caps;
+
+int g_tune_spt = 0;      // 0 = auto
+int g_tune_isplit = 0;   // 0 = auto
+
+// ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
+enum KClass { kcLayout = 0, kcPassA0, kcPassL, kcPassA, kcSquash, kcSoftmax, kcGrad, kcReduceDu, kcLoss, kcOther, kcCount };
+std::atomic<long> g_launches{0};
+int g_prof_on = 0;
+constexpr int kProfPool = 8192;
+cudaEvent_t g_prof_ev[kProfPool][2];
+int g_prof_cls[kProfPool];
+int g_prof_n = 0;
+bool g_prof_init = false;
+
+struct LaunchScope {          // brackets one kernel launch on `st`
+    int slot = -1;
+    cudaStream_t st;
+    LaunchScope(int cls, cudaStream_t s) : st(s) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (g_prof_on && g_prof_n < kProfPool) {
+            if (!g_prof_init) {
+                for (int i = 0; i < kProfPool; ++i) { cudaEventCreate(&g_prof_ev[i][0]); cudaEventCreate(&g_prof_ev[i][1]); }
+                g_prof_init = true;
+            }
+            slot = g_prof_n++;
+            g_prof_cls[slot] = cls;
+            cudaEventRecord(g_prof_ev[slot][0], st);
+        }
+    }
+    ~LaunchScope() { if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st); }
+};
+int pass_class(int mode) { return mode == kModeAUniform ? kcPassA0 : mode == kModeL ? kcPassL : kcPassA; }
+
+int pad_dim(int D) { return D <= 8 ? 8 : D <= 16 ? 16 : D <= 24 ? 24 : D <= 32 ? 32 : D <= 48 ? 48 : 0; }
+
+bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad) {
+    if (B < 0 || N <= 0 || C <= 0 || K != 8 || D <= 0 || D > 48 || R < 1 || R > 5 || C > 1024) return false;
+    p.B = B; p.N = N; p.C = C; p.K = K; p.D = D; p.R = R;
+    p.with_grad = with_grad != 0;
+    p.Reff = (C == 1) ? 1 : R;          // one class capsule: softmax == 1, iterations are no-ops
+    p.M = 2 * p.Reff - 1;
+    p.DP = pad_dim(D);
+    p.pad_w = (p.DP != D);
+    p.JW = C >= 7 ? 8 : C >= 3 ? 4 : 1;
+    if (C == 2) p.JW = 4;
+    p.JG = cdiv(C, p.JW);
+    p.nbt = B > 0 ? cdiv(B, 32) : 1;
+    int spt = g_tune_spt;
+    if (spt != 1 && spt != 2 && spt != 4) spt = (p.DP <= 16) ? 2 : 1;
+    if (p.DP > 16 && spt > 2) spt = 2;
+    if (p.DP > 32) spt = 1;
+    while (spt > 1 && p.nbt < spt) spt >>= 1;
+    p.SPT = spt;
+    p.ntg = cdiv(p.nbt, p.SPT);
+    // split the i range until there are ~4 CTAs per SM worth of work
+    int is = g_tune_isplit > 0 ? g_tune_isplit : cdiv(4 * 148, (long)p.JG * p.ntg);
+    const int max_is = cdiv(N, kPassIC);
+    if (is > max_is) is = max_is;
+    if (is > 64) is = 64;
+    if (is < 1) is = 1;
+    p.i_per_split = cdiv(cdiv(N, is), kPassIC) * kPassIC;
+    p.IS = cdiv(N, p.i_per_split);
+    p.xs = round64((size_t)p.nbt * C * p.DP * 32);
+    p.cs = round64((size_t)p.nbt * N * C * 32);
+    p.us = round64((size_t)p.nbt * N * K * 32);
+    size_t o = 0;
+    p.o_ut = o; o += p.us;
+    p.o_wp = o; o += p.pad_w ? round64((size_t)N * C * K * p.DP) : 0;
+    p.o_vsum = o; o += p.xs;
+    p.o_s = o; o += p.xs * p.Reff;
+    p.o_v = o; o += p.xs * p.Reff;
+    p.o_part = o; o += p.xs * p.IS;
+    p.o_c = o; o += p.cs * (p.with_grad ? (p.Reff > 1 ? p.Reff - 1 : 0) : (p.Reff > 1 ? 1 : 0));
+    p.o_beta = o; o += p.with_grad ? p.cs * (p.Reff > 1 ? p.Reff - 1 : 0) : 0;
+    p.o_tmp = o; o += p.with_grad && p.Reff > 1 ? p.cs : 0;
+    p.o_ds = o; o += p.with_grad ? p.xs * p.Reff : 0;
+    p.o_dupart = o; o += p.with_grad ? p.us * p.JG : 0;
+    p.total = o;
+    return true;
+}
+
+#define DISPATCH_DP(pl, CALL)                          \
+    switch ((pl).DP) {                                 \
+        case 8: { constexpr int DP_ = 8; CALL; } break;   \
+        case 16: { constexpr int DP_ = 16; CALL; } break; \
+        case 24: { constexpr int DP_ = 24; CALL; } break; \
+        case 32: { constexpr int DP_ = 32; CALL; } break; \
+        case 48: { constexpr int DP_ = 48; CALL; } break; \
+    }
+
+int launch_squash(const Plan& pl, const float* part, float scale, float* s_out, float* v_out, float* vsum,
+                  int accumulate, float* v_pub, cudaStream_t st) {
+    const long n = (long)pl.nbt * pl.C * 32;
+    LaunchScope ls_(kcSquash, st);
+    DISPATCH_DP(pl, (k_squash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, pl.IS, pl.xs, scale, s_out, v_out, vsum,
+                                                                  accumulate, v_pub, pl.B, pl.C, pl.D, pl.nbt)));
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_dsquash(const Plan& pl, const float* part, const float* grad_v, const int64_t* y, float mscale,
+                   const float* lgrad, const float* v_last, const float* s_in, float* ds_out, cudaStream_t st) {
+    const long n = (long)pl.nbt * pl.C * 32;
+    LaunchScope ls_(kcSquash, st);
+    DISPATCH_DP(pl, (k_dsquash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, pl.IS, pl.xs, grad_v, y, mscale, lgrad, v_last,
+                                                                   s_in, ds_out, pl.B, pl.C, pl.D, pl.nbt)));
+    LAUNCH_CHECK();
+    return 0;
+}
+
+bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+}  // namespace
+
+// ==============================================================================================
+// C ABI
+// ==============================================================================================
+extern "C" {
+
+int caps_abi_version(void) { return CAPS_ABI_VERSION; }
+
+const char* caps_last_error(void) { return g_err; }
+
+long caps_kernel_launch_count(void) { return g_launches.load(); }
+
+int caps_profile_collect(double* ms_by_class, long* count_by_class, int n_classes) {
+    for (int c = 0; c < n_classes; ++c) { if (ms_by_class) ms_by_class[c] = 0.0; if (count_by_class) count_by_class[c] = 0; }
+    for (int i = 0; i < g_prof_n; ++i) {
+        CUDA_TRY(cudaEventSynchronize(g_prof_ev[i][1]));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g_prof_ev[i][0], g_prof_ev[i][1]));
+        const int c = g_prof_cls[i];
+        if (c < n_classes) { if (ms_by_class) ms_by_class[c] += ms; if (count_by_class) count_by_class[c] += 1; }
+    }
+    g_prof_n = 0;
+    return 0;
+}
+
+int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream) {
+    if (iters <= 0 || !ms_out || !flops_out) return fail(CAPS_E_BADARG, "caps_fma_peak: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(float) * 1024));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    k_fma_peak<<<blocks, threads, 0, st>>>(sink, iters / 8 + 1, 0.999f, 1e-4f);      // warm-up
+    CUDA_TRY(cudaEventRecord(e0, st));
+    k_fma_peak<<<blocks, threads, 0, st>>>(sink, iters, 0.999f, 1e-4f);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, e0, e1));
+    *flops_out = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return 0;
+}
+
+int caps_set_tuning(const char* name, int value) {
+    if (name == nullptr) return fail(CAPS_E_BADARG, "caps_set_tuning: null name");
+    if (!strcmp(name, "profile")) { g_prof_on = value != 0; if (!g_prof_on) g_prof_n = 0; return 0; }
+    if (!strcmp(name, "spt")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) return fail(CAPS_E_BADARG, "spt must be 0,1,2,4");
+        g_tune_spt = value;
+        return 0;
+    }
+    if (!strcmp(name, "isplit")) {
+        if (value < 0 || value > 64) return fail(CAPS_E_BADARG, "isplit must be in [0,64]");
+        g_tune_isplit = value;
+        return 0;
+    }
+    return fail(CAPS_E_BADARG, "caps_set_tuning: unknown knob '%s'", name);
+}
+
+size_t caps_route_workspace_bytes(int B, int N, int C, int K, int D, int R, int with_grad) {
+    Plan pl;
+    if (!make_plan(pl, B, N, C, K, D, R, with_grad)) return 0;
+    return pl.total * sizeof(float);
+}
+
+int caps_route_forward(const float* u, const float* W, float* v, float* c_out, void* ws, size_t ws_bytes,
+                       int B, int N, int C, int K, int D, int R, int with_grad, void* stream) {
+    Plan pl;
+    if (!make_plan(pl, B, N, C, K, D, R, with_grad))
+        return fail(B < 0 || N <= 0 || C <= 0 || D <= 0 || R < 1 ? CAPS_E_BADARG : CAPS_E_UNSUPPORTED,
+                    "caps_route_forward: dims B=%d N=%d C=%d K=%d D=%d R=%d not supported (K must be 8, D<=48, R<=5)",
+                    B, N, C, K, D, R);
+    if (B == 0) return 0;
+    if (!u || !W || !v || !ws) return fail(CAPS_E_BADARG, "caps_route_forward: null pointer");
+    if (misaligned(u) || misaligned(W) || misaligned(ws))
+        return fail(CAPS_E_BADARG, "caps_route_forward: u, W and ws must be 16-byte aligned");
+    if (ws_bytes < pl.total * sizeof(float))
+        return fail(CAPS_E_WORKSPACE, "caps_route_forward: workspace %zu < %zu bytes", ws_bytes, pl.total * sizeof(float));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* w = static_cast<float*>(ws);
+    float* ut = w + pl.o_ut;
+    const float* Wp = W;
+    if (pl.pad_w) {
+        const long rows = (long)N * C * K;
+        { LaunchScope ls_(kcLayout, st); k_pad_w<<<cdiv(rows * pl.DP, 256), 256, 0, st>>>(W, w + pl.o_wp, rows, D, pl.DP); }
+        LAUNCH_CHECK();
+        Wp = w + pl.o_wp;
+    }
+    {
+        const long n = (long)pl.nbt * N * 32;
+        { LaunchScope ls_(kcLayout, st); k_prep_u<8><<<cdiv(n, 256), 256, 0, st>>>(u, ut, B, N, pl.nbt); }
+        LAUNCH_CHECK();
+    }
+    float* vsum = w + pl.o_vsum;
+    float* part = w + pl.o_part;
+    for (int r = 0; r < pl.Reff; ++r) {
+        float* s_r = w + pl.o_s + pl.xs * r;
+        float* v_r = w + pl.o_v + pl.xs * r;
+        const bool last = (r == pl.Reff - 1);
+        PassParams pp{};
+        pp.ut = ut; pp.W = Wp; pp.N = N; pp.C = C; pp.nbt = pl.nbt; pp.i_per_split = pl.i_per_split;
+        int rc;
+        if (r == 0) {
+            pp.out = part;
+            { LaunchScope ls_(pass_class(kModeAUniform), st); rc = launch_pass(pl, kModeAUniform, pp, st); } if (rc) return rc;
+            if ((rc = launch_squash(pl, part, 1.f / (float)C, s_r, v_r, vsum, 0, last ? v : nullptr, st))) return rc;
+        } else {
+            float* c_r = w + pl.o_c + (pl.with_grad ? pl.cs * (r - 1) : 0);
+            pp.X = vsum; pp.out = c_r;
+            { LaunchScope ls_(pass_class(kModeL), st); rc = launch_pass(pl, kModeL, pp, st); } if (rc) return rc;
+            const long n = (long)pl.nbt * N * 32;
+            { LaunchScope ls_(kcSoftmax, st); k_softmax<<<cdiv(n, 128), 128, 0, st>>>(c_r, (last ? c_out : nullptr), B, N, C, pl.nbt); }
+            LAUNCH_CHECK();
+            pp.X = nullptr; pp.coef = c_r; pp.out = part;
+            { LaunchScope ls_(pass_class(kModeA), st); rc = launch_pass(pl, kModeA, pp, st); } if (rc) return rc;
+            if ((rc = launch_squash(pl, part, 1.f, s_r, v_r, vsum, 1, last ? v : nullptr, st))) return rc;
+        }
+    }
+    if (c_out != nullptr && pl.Reff == 1) {      // R == 1 or C == 1: the couplings are the constant 1/C
+        const long n = (long)B * N * C;
+        { LaunchScope ls_(kcOther, st); k_fill<<<cdiv(n, 256), 256, 0, st>>>(c_out, 1.f / (float)C, n); }
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int caps_route_backward(const float* u, const float* W, const float* grad_v, const int64_t* y, float margin_scale,
+                        const float* loss_grad_dev, float* du, float* dW, void* ws, size_t ws_bytes,
+                        int B, int N, int C, int K, int D, int R, void* stream) {
+    (void)u;
+    Plan pl;
+    if (!make_plan(pl, B, N, C, K, D, R, 1))
+        return fail(CAPS_E_UNSUPPORTED, "caps_route_backward: dims B=%d N=%d C=%d K=%d D=%d R=%d not supported", B, N, C, K, D, R);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!W || !dW) return fail(CAPS_E_BADARG, "caps_route_backward: null pointer");
+    if (B == 0) {
+        CUDA_TRY(cudaMemsetAsync(dW, 0, (size_t)N * C * K * D * sizeof(float), st));
+        return 0;
+    }
+    if (!ws) return fail(CAPS_E_BADARG, "caps_route_backward: null workspace");
+    if (misaligned(W) || misaligned(ws) || misaligned(dW) || (du && misaligned(du)))
+        return fail(CAPS_E_BADARG, "caps_route_backward: W, dW, du and ws must be 16-byte aligned");
+    if (ws_bytes < pl.total * sizeof(float))
+        return fail(CAPS_E_WORKSPACE, "caps_route_backward: workspace %zu < %zu bytes", ws_bytes, pl.total * sizeof(float));
+    float* w = static_cast<float*>(ws);
+    const float* ut = w + pl.o_ut;
+    const float* Wp = pl.pad_w ? w + pl.o_wp : W;
+    float* part = w + pl.o_part;
+    float* tmp = w + pl.o_tmp;
+    const int Re = pl.Reff;
+    int rc;
+    // top: dv = grad_v + margin gradient ; ds^{R-1}
+    if ((rc = launch_dsquash(pl, nullptr, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),
+                             w + pl.o_s + pl.xs * (Re - 1), w + pl.o_ds + pl.xs * (Re - 1), st)))
+        return rc;
+    for (int r = Re - 1; r >= 1; --r) {
+        const float* c_r = w + pl.o_c + pl.cs * (r - 1);
+        float* beta_r = w + pl.o_beta + pl.cs * (r - 1);
+        const float* beta_next = (r == Re - 1) ? nullptr : w + pl.o_beta + pl.cs * r;
+        PassParams pp{};
+        pp.ut = ut; pp.W = Wp; pp.N = N; pp.C = C; pp.nbt = pl.nbt; pp.i_per_split = pl.i_per_split;
+        pp.X = w + pl.o_ds + pl.xs * r; pp.out = tmp;                       // dc = u_hat . ds^r
+        { LaunchScope ls_(pass_class(kModeL), st); rc = launch_pass(pl, kModeL, pp, st); } if (rc) return rc;
+        const long n = (long)pl.nbt * N * 32;
+        { LaunchScope ls_(kcSoftmax, st); k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt); }
+        LAUNCH_CHECK();
+        pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
+        { LaunchScope ls_(pass_class(kModeA), st); rc = launch_pass(pl, kModeA, pp, st); } if (rc) return rc;
+        if ((rc = launch_dsquash(pl, part, nullptr, nullptr, 0.f, nullptr, nullptr, w + pl.o_s + pl.xs * (r - 1),
+                                 w + pl.o_ds + pl.xs * (r - 1), st)))
+            return rc;
+    }
+    GradParams gp{};
+    gp.ut = ut; gp.W = Wp; gp.dW = dW; gp.du_part = w + pl.o_dupart;
+    gp.N = N; gp.C = C; gp.D = D; gp.nbt = pl.nbt;
+    int m = 0;
+    for (int r = 0; r < Re; ++r) {                                          // c^r (x) ds^r
+        gp.coef[m] = (r == 0) ? nullptr : w + pl.o_c + pl.cs * (r - 1);
+        gp.cconst[m] = 1.f / (float)C;
+        gp.X[m] = w + pl.o_ds + pl.xs * r;
+        ++m;
+    }
+    for (int r = 1; r < Re; ++r) {                                          // beta^r (x) v^{r-1}
+        gp.coef[m] = w + pl.o_beta + pl.cs * (r - 1);
+        gp.cconst[m] = 0.f;
+        gp.X[m] = w + pl.o_v + pl.xs * (r - 1);
+        ++m;
+    }
+    { LaunchScope ls_(kcGrad, st); rc = launch_grad(pl, gp, st); } if (rc) return rc;
+    if (du != nullptr) {
+        const long n = (long)pl.nbt * N * 32;
+        { LaunchScope ls_(kcReduceDu, st); k_reduce_du<8><<<cdiv(n, 128), 128, 0, st>>>(gp.du_part, pl.JG, du, B, N, pl.nbt); }
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int caps_margin_loss(const float* v, const int64_t* y, float scale, float* loss, float* scores_out,
+                     int B, int C, int D, void* stream) {
+    if (!v || !y || !loss || B < 0 || C <= 0 || D <= 0) return fail(CAPS_E_BADARG, "caps_margin_loss: bad argument");
+    { LaunchScope ls_(kcLoss, static_cast<cudaStream_t>(stream)); k_margin_loss<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(v, y, scale, loss, scores_out, B, C, D); }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int caps_squash(const float* x, float* y, long rows, int D, void* stream) {
+    if (!x || !y || rows < 0 || D <= 0) return fail(CAPS_E_BADARG, "caps_squash: bad argument");
+    if (rows == 0) return 0;
+    { LaunchScope ls_(kcOther, static_cast<cudaStream_t>(stream)); k_squash_rows<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, D); }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, int D, void* stream) {
+    if (!x || !dy || !dx || rows < 0 || D <= 0) return fail(CAPS_E_BADARG, "caps_squash_backward: bad argument");
+    if (rows == 0) return 0;
+    { LaunchScope ls_(kcOther, static_cast<cudaStream_t>(stream)); k_squash_rows_bwd<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, rows, D); }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- host-buffer step ------------------------------------------------------------------------
+namespace {
+struct HostStepLayout { size_t o_u, o_y, o_v, o_du, o_loss, o_ws, total; };
+bool host_step_layout(HostStepLayout& L, int B, int N, int C, int K, int D, int R) {
+    const size_t wsb = caps_route_workspace_bytes(B, N, C, K, D, R, 1);
+    if (wsb == 0) return false;
+    auto r256 = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    size_t o = 0;
+    L.o_u = o; o += r256((size_t)B * N * K * 4);
+    L.o_y = o; o += r256((size_t)B * 8);
+    L.o_v = o; o += r256((size_t)B * C * D * 4);
+    L.o_du = o; o += r256((size_t)B * N * K * 4);
+    L.o_loss = o; o += 256;
+    L.o_ws = o; o += r256(wsb);
+    L.total = o;
+    return true;
+}
+}  // namespace
+
+size_t caps_route_step_host_scratch_bytes(int B, int N, int C, int K, int D, int R) {
+    HostStepLayout L;
+    return host_step_layout(L, B, N, C, K, D, R) ? L.total : 0;
+}
+
+int caps_route_step_host(const float* u_host, const int64_t* y_host, const float* W_dev, float* loss_host,
+                         float* v_host, float* du_host, float* dW_dev, void* dev_scratch, size_t scratch_bytes,
+                         int B, int N, int C, int K, int D, int R, void* stream) {
+    HostStepLayout L;
+    if (!host_step_layout(L, B, N, C, K, D, R)) return fail(CAPS_E_UNSUPPORTED, "caps_route_step_host: dims not supported");
+    if (!u_host || !y_host || !W_dev || !loss_host || !dW_dev || !dev_scratch || B <= 0)
+        return fail(CAPS_E_BADARG, "caps_route_step_host: bad argument");
+    if (scratch_bytes < L.total) return fail(CAPS_E_WORKSPACE, "caps_route_step_host: scratch %zu < %zu", scratch_bytes, L.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* base = static_cast<char*>(dev_scratch);
+    float* u_d = reinterpret_cast<float*>(base + L.o_u);
+    int64_t* y_d = reinterpret_cast<int64_t*>(base + L.o_y);
+    float* v_d = reinterpret_cast<float*>(base + L.o_v);
+    float* du_d = reinterpret_cast<float*>(base + L.o_du);
+    float* loss_d = reinterpret_cast<float*>(base + L.o_loss);
+    void* ws = base + L.o_ws;
+    const size_t wsb = L.total - L.o_ws;
+    CUDA_TRY(cudaMemcpyAsync(u_d, u_host, (size_t)B * N * K * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(y_d, y_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    int rc;
+    if ((rc = caps_route_forward(u_d, W_dev, v_d, nullptr, ws, wsb, B, N, C, K, D, R, 1, stream))) return rc;
+    const float scale = 1.f / (float)B;
+    if ((rc = caps_margin_loss(v_d, y_d, scale, loss_d, nullptr, B, C, D, stream))) return rc;
+    if ((rc = caps_route_backward(u_d, W_dev, nullptr, y_d, scale, nullptr, du_host ? du_d : nullptr, dW_dev, ws, wsb,
+                                  B, N, C, K, D, R, stream)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(loss_host, loss_d, 4, cudaMemcpyDeviceToHost, st));
+    if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, v_d, (size_t)B * C * D * 4, cudaMemcpyDeviceToHost, st));
+    if (du_host) CUDA_TRY(cudaMemcpyAsync(du_host, du_d, (size_t)B * N * K * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,124 @@
+/* caps_routing.h -- C ABI of the B200-native capsule dynamic-routing path.
+ *
+ * This is the drop-in boundary for ONE path of Cranial-XIX/cs231-capsule-yolo-traffic-sign-detection:
+ * the caps->caps branch of `CapsuleLayer` (reference models.py:46-83) plus the margin-loss
+ * gradient that feeds it (reference loss_fns.py:11-23, models.py:117).  The reference has no
+ * FFI of its own -- its boundary is the Python class -- so these entry points are what a ctypes
+ * binding behind that class calls (the in-repo binding is
+ * cs231_capsule_yolo_traffic_sign_detection_b200/_cabi.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.  All `float*` are fp32, row-major,
+ *     contiguous, 16-byte aligned.  Unless a function says HOST, pointers are DEVICE pointers on
+ *     the current CUDA device and work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *     nothing synchronises the host.
+ *   - dims: B batch, N = n_nodes (input capsules), C = n_caps (output capsules), K = in_C,
+ *     D = out_C, R = n_iter                                   (reference models.py:47-58)
+ *   - tensors:  u [B,N,K]   W [N,C,K,D] (= route_weights[0])   v [B,C,D] (= output[:,0,:,0,:])
+ *               c [B,N,C] (last-iteration coupling coefficients)   y [B] int64 labels
+ *   - return value: 0 on success; CAPS_E_* (<0) for argument errors; a positive cudaError_t if a
+ *     CUDA call failed.  caps_last_error() returns a thread-local message for the last failure.
+ *   - the library keeps no global mutable state apart from the caps_set_tuning() knobs;
+ *     launchers are re-entrant; the caller owns every
+ *     buffer (inputs, outputs, workspace) for the duration of the enqueued work.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef CAPS_ROUTING_H_
+#define CAPS_ROUTING_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPS_ABI_VERSION 1
+
+#define CAPS_E_BADARG     (-1)   /* null pointer / non-positive dim / misaligned pointer        */
+#define CAPS_E_UNSUPPORTED (-2)  /* K != 8, D > 48, R > 5, C > 1024: shapes with no kernel       */
+#define CAPS_E_WORKSPACE  (-3)   /* workspace smaller than caps_route_workspace_bytes() says     */
+#define CAPS_E_STATE      (-4)   /* backward called on a workspace that holds no forward state   */
+
+/* ABI version of the loaded library (== CAPS_ABI_VERSION of the header it was built from). */
+int caps_abi_version(void);
+
+/* Thread-local description of the last non-zero return on this thread ("" if none). */
+const char* caps_last_error(void);
+
+/* Bytes of device workspace caps_route_forward/backward need for these dims.  with_grad != 0
+ * sizes it to also hold the forward state the backward pass reads (per-iteration capsule sums and
+ * coupling coefficients) and the backward scratch.  Returns 0 for unsupported dims. */
+size_t caps_route_workspace_bytes(int B, int N, int C, int K, int D, int R, int with_grad);
+
+/* Forward of the routing branch: replaces reference models.py:71-79 (+ :83).
+ *   u_hat = u.W ; R x { c = softmax_j(b) ; s = sum_i c u_hat ; v = squash(s) ; b += u_hat.v }
+ *   v      out [B,C,D]   class capsules of the last iteration
+ *   c_out  out [B,N,C]   last-iteration couplings, or NULL (only tests want it)
+ *   ws     workspace of >= caps_route_workspace_bytes(..., with_grad) bytes, 256-byte aligned.
+ *          With with_grad != 0 it holds the state caps_route_backward needs; keep it (and u, W)
+ *          unchanged until that call. */
+int caps_route_forward(const float* u, const float* W, float* v, float* c_out,
+                       void* ws, size_t ws_bytes,
+                       int B, int N, int C, int K, int D, int R, int with_grad, void* stream);
+
+/* Backward through ALL R iterations (the reference never detaches; autograd of models.py:71-79),
+ * with the margin-loss gradient optionally fused:
+ *   g = grad_v (if non-NULL)  +  d/dv [ margin_loss(|v|, y) * margin_scale * lg ] (if y non-NULL)
+ *       margin term: reference loss_fns.py:12-17,23 on scores = |v| (models.py:117);
+ *       margin_scale is the reference's 1/y.size(0); lg = *loss_grad_dev if that DEVICE scalar
+ *       is non-NULL (the upstream d/d loss autograd hands over; avoids a host sync), else 1.
+ *   du  out [B,N,K]     d loss / d u      (or NULL to skip writing it)
+ *   dW  out [N,C,K,D]   d loss / d W, summed over the batch; OVERWRITTEN, not accumulated
+ * `ws` must be the workspace a with_grad forward with the same dims, u and W filled.
+ * Summation orders are fixed: results are bit-reproducible run to run. */
+int caps_route_backward(const float* u, const float* W, const float* grad_v, const int64_t* y,
+                        float margin_scale, const float* loss_grad_dev, float* du, float* dW,
+                        void* ws, size_t ws_bytes,
+                        int B, int N, int C, int K, int D, int R, void* stream);
+
+/* Margin loss value: sum_{b,j} [ T relu(0.9-m)^2 + 0.5 (1-T) relu(m-0.1)^2 ] * scale with
+ * m = |v[b,j,:]|, T = (y[b]==j).  Replaces reference models.py:117 + loss_fns.py:12-17,23
+ * (recon term off).  loss: one float (device).  scores_out: [B,C] or NULL. */
+int caps_margin_loss(const float* v, const int64_t* y, float scale, float* loss,
+                     float* scores_out, int B, int C, int D, void* stream);
+
+/* squash over the last dim of a [rows, D] array (reference models.py:64-67), any D >= 1.
+ * Used by the primary-capsule branch (models.py:82).  y may alias x. */
+int caps_squash(const float* x, float* y, long rows, int D, void* stream);
+/* its backward: dx = d squash(x)/dx applied to dy. */
+int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, int D, void* stream);
+
+/* HOST-buffer step, the end-to-end call: copies u (and y) host->device, runs forward, margin
+ * loss, fused backward, and copies loss (and, if non-NULL, v / du / dW) device->host, all on
+ * `stream`, then synchronises that stream.  u_host/y_host/..._host are HOST pointers (pinned for
+ * speed).  W_dev/dW_dev stay on the device (weights live there).  dev_scratch is a device
+ * buffer of >= caps_route_step_host_scratch_bytes(...) bytes. */
+size_t caps_route_step_host_scratch_bytes(int B, int N, int C, int K, int D, int R);
+int caps_route_step_host(const float* u_host, const int64_t* y_host, const float* W_dev,
+                         float* loss_host, float* v_host, float* du_host, float* dW_dev,
+                         void* dev_scratch, size_t scratch_bytes,
+                         int B, int N, int C, int K, int D, int R, void* stream);
+
+/* Measurement helpers (bench.py).  caps_kernel_launch_count: kernels this library has launched in
+ * this process.  With caps_set_tuning("profile", 1) every launch is bracketed by CUDA events on
+ * its own stream; caps_profile_collect synchronises them, sums milliseconds / launch counts per
+ * kernel class (0 layout, 1 pass-A0, 2 pass-L, 3 pass-A, 4 squash, 5 softmax, 6 grad, 7 du-reduce,
+ * 8 loss, 9 other) and resets.  Profiling state is process-global: single-threaded use only.
+ * caps_fma_peak: times `iters` x 16 dependent-chain FFMAs per thread on a full grid and returns
+ * milliseconds and the flop count (the fp32-FMA roofline denominator). */
+long caps_kernel_launch_count(void);
+int caps_profile_collect(double* ms_by_class, long* count_by_class, int n_classes);
+int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
+
+/* Tuning knobs (process-wide, read at call time; defaults are chosen per shape).
+ *   name = "spt"  samples per thread in the pass kernels (1, 2 or 4; 0 = auto)
+ *   name = "isplit" forced number of splits of the N range (0 = auto)
+ *   name = "profile" 1: bracket every launch with CUDA events (see caps_profile_collect)
+ * Returns 0, or CAPS_E_BADARG for an unknown name/value.  Meant for benchmarks and tests. */
+int caps_set_tuning(const char* name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPS_ROUTING_H_ */

@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI / the CapsuleLayer module) against the oracle and
+the reference-generated golden fixtures.  Needs a B200: run with `pytest -m gpu`.
+
+Tolerances are the north_star's: rel 1e-5 on v (and c, loss), rel 1e-4 on gradients, where
+rel = max|a-b| / max|b| and b is the reference's fp64 result (fp32 result for the fixtures' fp32
+copies, which differ from fp64 by up to ~1e-6 themselves)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_V = 1e-5
+TOL_G = 1e-4
+
+
+@pytest.fixture(scope='module')
+def capsb():
+    import cs231_capsule_yolo_traffic_sign_detection_b200 as m
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    m._cabi.lib()                       # raises if the CUDA library is missing: no silent fallback
+    return m
+
+
+def cuda_step(capsb, u, W, y, R, want_c=True, grad_v_extra=None):
+    """fwd (+c) + fused margin loss + bwd through the public API; returns numpy dict."""
+    dev = torch.device('cuda')
+    ut = torch.from_numpy(u).to(dev).requires_grad_(True)
+    Wt = torch.from_numpy(W)[None].to(dev).requires_grad_(True)
+    yt = torch.from_numpy(y).to(dev)
+    out = {}
+    if want_c:
+        with torch.no_grad():
+            _, c = capsb.dynamic_routing(ut, Wt, R, return_couplings=True)
+        out['c'] = c.cpu().numpy()
+    v, loss = capsb.routing_margin_loss(ut, Wt, yt, R)
+    total = loss
+    if grad_v_extra is not None:
+        total = loss + (v * torch.from_numpy(grad_v_extra).to(dev)).sum()
+    total.backward()
+    torch.cuda.synchronize()
+    out.update(v=v.detach().cpu().numpy(), loss=float(loss), du=ut.grad.cpu().numpy(),
+               dW=Wt.grad[0].cpu().numpy())
+    return out
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_golden_fixture(capsb, name):
+    g, (u, W, y) = load_golden(name)
+    r = cuda_step(capsb, u, W, y, g['R'])
+    st = int(g['probe_stride'])
+    assert rel_err(r['v'], g['v64']) < TOL_V
+    assert abs(r['loss'] - float(g['loss64'])) < TOL_V * max(1.0, abs(float(g['loss64'])))
+    assert rel_err(r['du'], g['du64']) < TOL_G
+    assert rel_err(r['dW'].reshape(-1)[::st], g['dW64_probe']) < TOL_G
+    if 'c64' in g:
+        assert rel_err(r['c'], g['c64']) < TOL_V
+        assert rel_err(r['dW'], g['dW']) < TOL_G          # full dW against the reference's fp32 run
+    else:
+        assert rel_err(r['c'].reshape(-1)[::st], g['c64_probe']) < TOL_V
+    assert np.allclose(r['c'].sum(-1), 1.0, atol=1e-5)    # couplings are a distribution over j
+
+
+@pytest.mark.parametrize('dims', [
+    (37, 1296, 43, 8, 16, 3),     # CapsuleNet routing shape, ragged lane tile
+    (64, 1152, 43, 8, 16, 3),     # BASELINE.json config 2 shape
+    (100, 130, 43, 8, 16, 2),
+    (70, 512, 1, 8, 5, 3),        # DarkCapsuleNet head
+    (33, 64, 10, 8, 16, 4),
+    (5, 50, 43, 8, 21, 3),        # DarkCapsuleNet3 head dims
+    (6, 40, 49, 8, 48, 3),        # DarkCapsuleNet2 head dims
+    (40, 96, 43, 8, 32, 5),       # sweep corner: D=32, R=5
+    (3, 7, 3, 8, 4, 3),           # tiny / odd everything
+    (2, 9, 2, 8, 24, 2),
+])
+def test_against_c_oracle_fp64(capsb, dims):
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = dims
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=sum(dims))
+    ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R)
+    r = cuda_step(capsb, u, W, y, R)
+    assert rel_err(r['v'], ref['v']) < TOL_V
+    assert rel_err(r['c'], ref['c']) < TOL_V
+    assert abs(r['loss'] - ref['loss']) < TOL_V * max(1.0, abs(ref['loss']))
+    assert rel_err(r['du'], ref['du']) < TOL_G
+    assert rel_err(r['dW'], ref['dW']) < TOL_G
+
+
+def test_external_grad_v_and_unfused_loss(capsb):
+    """Gradient arriving through autograd (decoder / coordinate losses feed v directly:
+    reference models.py:122, loss_fns.py:197) plus the unfused margin loss written with torch ops
+    like reference loss_fns.py:11-23 must match the fused kernel path and the oracle."""
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = 19, 80, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=5)
+    gext = np.random.default_rng(6).standard_normal((B, C, D)).astype(np.float32) * 0.01
+    ref = onp.routing_step(u.astype(np.float64), W.astype(np.float64), y, R, grad_v_extra=gext.astype(np.float64))
+    fused = cuda_step(capsb, u, W, y, R, want_c=False, grad_v_extra=gext)
+    assert rel_err(fused['du'], ref['du']) < TOL_G
+    assert rel_err(fused['dW'], ref['dW']) < TOL_G
+
+    dev = torch.device('cuda')
+    ut = torch.from_numpy(u).to(dev).requires_grad_(True)
+    Wt = torch.from_numpy(W)[None].to(dev).requires_grad_(True)
+    v = capsb.dynamic_routing(ut, Wt, R)
+    scores = (v ** 2).sum(dim=-1) ** 0.5
+    onehot = torch.eye(C, device=dev).index_select(0, torch.from_numpy(y).to(dev))
+    margin = onehot * torch.relu(0.9 - scores) ** 2 + 0.5 * (1 - onehot) * torch.relu(scores - 0.1) ** 2
+    loss = margin.sum() / B + (v * torch.from_numpy(gext).to(dev)).sum()
+    loss.backward()
+    assert rel_err(ut.grad.cpu().numpy(), ref['du']) < TOL_G
+    assert rel_err(Wt.grad[0].cpu().numpy(), ref['dW']) < TOL_G
+    assert abs(float(margin.sum() / B) - ref['loss']) < 1e-5
+
+
+def test_bit_reproducible_and_tuning_invariant(capsb):
+    """Fixed summation orders: same bits run to run; samples-per-thread / i-split only regroup
+    independent work (v is bit-identical per sample when the i-split is unchanged)."""
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = 150, 200, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=9)
+    base = cuda_step(capsb, u, W, y, R, want_c=False)
+    again = cuda_step(capsb, u, W, y, R, want_c=False)
+    for k in ('v', 'du', 'dW'):
+        assert np.array_equal(base[k], again[k]), k
+    try:
+        for spt in (1, 2, 4):
+            capsb._cabi.set_tuning('spt', spt)
+            capsb._cabi.set_tuning('isplit', 5)
+            r = cuda_step(capsb, u, W, y, R, want_c=False)
+            if spt == 1:
+                first = r
+            assert np.array_equal(r['v'], first['v'])
+            assert np.array_equal(r['du'], first['du'])
+            assert rel_err(r['dW'], base['dW']) < 1e-5
+        capsb._cabi.set_tuning('spt', 0)
+        for isplit in (1, 3, 64):
+            capsb._cabi.set_tuning('isplit', isplit)
+            r = cuda_step(capsb, u, W, y, R, want_c=False)
+            assert rel_err(r['v'], base['v']) < 1e-5
+            assert rel_err(r['dW'], base['dW']) < 1e-5
+    finally:
+        capsb._cabi.set_tuning('spt', 0)
+        capsb._cabi.set_tuning('isplit', 0)
+
+
+def test_batch_permutation_and_additivity_at_full_size(capsb):
+    """Size-independent properties at BASELINE.json's shape (1152 -> 43x16, R=3), where the
+    oracle is too slow: samples are independent, so (a) permuting the batch permutes v and du
+    bit-exactly, (b) dW of a batch is the sum of the dW of its halves (fp32 reassociation only),
+    (c) a sample's result does not depend on its batch-mates."""
+    from oracle import routing_np as onp
+    from oracle import routing_c as oc
+    B, N, C, K, D, R = 1024, 1152, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=3)
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cpu').manual_seed(1)
+    gext = (torch.randn(B, C, D, generator=g) * 0.01).numpy()
+
+    def run(idx):
+        ut = torch.from_numpy(u[idx]).to(dev).requires_grad_(True)
+        Wt = torch.from_numpy(W)[None].to(dev).requires_grad_(True)
+        v = capsb.dynamic_routing(ut, Wt, R)
+        (v * torch.from_numpy(gext[idx]).to(dev)).sum().backward()
+        return v.detach().cpu().numpy(), ut.grad.cpu().numpy(), Wt.grad[0].cpu().numpy()
+
+    ident = np.arange(B)
+    perm = np.random.default_rng(0).permutation(B)
+    v0, du0, dW0 = run(ident)
+    v1, du1, dW1 = run(perm)
+    assert np.array_equal(v1, v0[perm])
+    assert np.array_equal(du1, du0[perm])
+    assert rel_err(dW1, dW0) < 1e-5
+    va, dua, dWa = run(ident[:500])
+    vb, dub, dWb = run(ident[500:])
+    assert np.array_equal(va, v0[:500]) and np.array_equal(vb, v0[500:])
+    assert rel_err(dWa + dWb, dW0) < 1e-5
+    # spot-check a few samples of the big batch against the fp64 oracle
+    pick = np.array([0, 499, 500, 1023])
+    ref = oc.routing_step(u[pick].astype(np.float64), W.astype(np.float64), None, R,
+                          grad_v_extra=gext[pick].astype(np.float64))
+    assert rel_err(v0[pick], ref['v']) < TOL_V
+    assert rel_err(du0[pick], ref['du']) < TOL_G
+
+
+def test_edge_cases(capsb):
+    from oracle import routing_np as onp
+    dev = torch.device('cuda')
+    # empty batch
+    W = torch.randn(1, 12, 5, 8, 16, device=dev, requires_grad=True)
+    u = torch.zeros(0, 12, 8, device=dev, requires_grad=True)
+    v = capsb.dynamic_routing(u, W, 3)
+    assert v.shape == (0, 5, 16)
+    v.sum().backward()
+    assert torch.count_nonzero(W.grad) == 0
+    # a zero capsule sum is 0/0 in the reference's squash (models.py:64-67): NaN, not clamped
+    v = capsb.dynamic_routing(torch.zeros(2, 12, 8, device=dev), W.detach(), 3)
+    assert torch.isnan(v).all()
+    # single class capsule: routing iterations are no-ops (SURVEY 3.3 iv)
+    u, Wn, _ = onp.make_inputs(4, 64, 1, 8, 5, seed=2)
+    a = capsb.dynamic_routing(torch.from_numpy(u).to(dev), torch.from_numpy(Wn)[None].to(dev), 1)
+    b = capsb.dynamic_routing(torch.from_numpy(u).to(dev), torch.from_numpy(Wn)[None].to(dev), 3)
+    assert torch.equal(a, b)
+    # unsupported shapes fail loudly
+    with pytest.raises(RuntimeError):
+        capsb.dynamic_routing(torch.zeros(2, 4, 6, device=dev), torch.zeros(1, 4, 3, 6, 16, device=dev), 3)
+    with pytest.raises(RuntimeError):
+        capsb.dynamic_routing(torch.zeros(2, 4, 8), torch.zeros(1, 4, 3, 8, 16), 3)   # CPU tensors
+
+
+def test_host_step_matches_device_path(capsb):
+    """The HOST-buffer entry point (what bench.py's e2e leg times) gives the device path's bits."""
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = 48, 96, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=8)
+    ref = cuda_step(capsb, u, W, y, R, want_c=False)
+    dev = torch.device('cuda')
+    step = capsb.HostStep(B, N, C, K, D, R)
+    Wd = torch.from_numpy(W).to(dev)
+    dWd = torch.empty_like(Wd)
+    uh = torch.from_numpy(u).pin_memory()
+    yh = torch.from_numpy(y).pin_memory()
+    vh = torch.empty(B, C, D).pin_memory()
+    duh = torch.empty(B, N, K).pin_memory()
+    loss = step(uh, yh, Wd, dWd, v_host=vh, du_host=duh)
+    assert abs(float(loss[0]) - ref['loss']) < 1e-7
+    assert np.array_equal(vh.numpy(), ref['v'])
+    assert np.array_equal(duh.numpy(), ref['du'])
+    assert np.array_equal(dWd.cpu().numpy(), ref['dW'])
+
+
+def test_squash_kernel(capsb):
+    from oracle import routing_np as onp
+    dev = torch.device('cuda')
+    x = torch.randn(1000, 8, device=dev, requires_grad=True)
+    layer = capsb.CapsuleLayer(None, n_caps=3, n_nodes=4, in_C=8, out_C=16)
+    y = layer.squash(x)
+    ref = onp.squash(x.detach().cpu().numpy().astype(np.float64))
+    assert rel_err(y.detach().cpu().numpy(), ref) < 1e-6
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    gref = onp.squash_bwd(x.detach().cpu().numpy().astype(np.float64), gy.cpu().numpy().astype(np.float64))
+    assert rel_err(x.grad.cpu().numpy(), gref) < 1e-5
