@@ -191,6 +191,7 @@ def main_gpu(args, rank, world, device):
     du = torch.empty(B, N, K, device=device)
     dW = torch.empty_like(W)
     loss = torch.empty((), device=device)
+    lscr = torch.empty(_cabi.MARGIN_SCRATCH_FLOATS, device=device)
     nbytes = L.caps_route_workspace_bytes(B, N, C, K, D, R, 1)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream().cuda_stream
@@ -198,7 +199,7 @@ def main_gpu(args, rank, world, device):
 
     def step_device():
         _cabi.check(L.caps_route_forward(P(u), P(W), P(v), None, P(ws), nbytes, B, N, C, K, D, R, 1, stream), 'fwd')
-        _cabi.check(L.caps_margin_loss(P(v), P(y), 1.0 / B, P(loss), None, B, C, D, stream), 'loss')
+        _cabi.check(L.caps_margin_loss(P(v), P(y), 1.0 / B, P(loss), None, P(lscr), B, C, D, stream), 'loss')
         _cabi.check(L.caps_route_backward(P(u), P(W), None, P(y), 1.0 / B, None, P(du), P(dW), P(ws), nbytes,
                                           B, N, C, K, D, R, stream), 'bwd')
         if world > 1:

@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcaps_routing.so')
 
 ABI_VERSION = 1
+MARGIN_SCRATCH_FLOATS = 2048
 
 # every symbol include/caps_routing.h declares: name -> (restype, argtypes)
 _vp, _i, _f, _sz, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_long
@@ -20,7 +21,7 @@ SYMBOLS = {
     'caps_route_workspace_bytes': (_sz, [_i] * 7),
     'caps_route_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _sz] + [_i] * 7 + [_vp]),
     'caps_route_backward': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
-    'caps_margin_loss': (_i, [_vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp]),
+    'caps_margin_loss': (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'caps_squash': (_i, [_vp, _vp, _l, _i, _vp]),
     'caps_squash_backward': (_i, [_vp, _vp, _vp, _l, _i, _vp]),
     'caps_route_step_host_scratch_bytes': (_sz, [_i] * 6),

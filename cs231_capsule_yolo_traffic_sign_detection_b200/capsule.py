@@ -113,8 +113,9 @@ class _RoutingMarginLossFn(torch.autograd.Function):
         B, C, D = v.shape
         y = y.to(device=u.device, dtype=torch.int64).contiguous()
         loss = torch.empty((), device=u.device, dtype=torch.float32)
+        scratch = torch.empty((_cabi.MARGIN_SCRATCH_FLOATS,), device=u.device, dtype=torch.float32)
         with torch.cuda.device(u.device):
-            _cabi.check(L.caps_margin_loss(_ptr(v), _ptr(y), 1.0 / B, _ptr(loss), None, B, C, D, _stream()),
+            _cabi.check(L.caps_margin_loss(_ptr(v), _ptr(y), 1.0 / B, _ptr(loss), None, _ptr(scratch), B, C, D, _stream()),
                         'caps_margin_loss')
         if with_grad:
             ctx.save_for_backward(u_c, W_c, y)

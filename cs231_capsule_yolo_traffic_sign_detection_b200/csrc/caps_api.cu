@@ -26,6 +26,7 @@ using namespace caps;
 
 int g_tune_spt = 0;      // 0 = auto
 int g_tune_isplit = 0;   // 0 = auto
+int g_tune_tc = 1;       // 1 = use the tcgen05 pass kernel where it applies, 0 = FFMA kernel only
 
 // ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
 enum KClass { kcLayout = 0, kcPassA0, kcPassL, kcPassA, kcSquash, kcSoftmax, kcGrad, kcReduceDu, kcLoss, kcOther, kcCount };
@@ -85,10 +86,13 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     if (is < 1) is = 1;
     p.i_per_split = cdiv(cdiv(N, is), kPassIC) * kPassIC;
     p.IS = cdiv(N, p.i_per_split);
+    p.use_tc = g_tune_tc != 0 && D == 16 && C >= 4;
     p.xs = round64((size_t)p.nbt * C * p.DP * 32);
     p.cs = round64((size_t)p.nbt * N * C * 32);
     p.us = round64((size_t)p.nbt * N * K * 32);
     size_t o = 0;
+    p.o_ua = o; o += p.use_tc ? round64(tc_ua_floats(B, N)) : 0;
+    p.o_wb = o; o += p.use_tc ? round64(tc_wb_floats(N, C)) : 0;
     p.o_ut = o; o += p.us;
     p.o_wp = o; o += p.pad_w ? round64((size_t)N * C * K * p.DP) : 0;
     p.o_vsum = o; o += p.xs;
@@ -131,6 +135,13 @@ int launch_dsquash(const Plan& pl, const float* part, const float* grad_v, const
                                                                    s_in, ds_out, pl.B, pl.C, pl.D, pl.nbt)));
     LAUNCH_CHECK();
     return 0;
+}
+
+// one pass on whichever engine the plan selected
+int run_pass(const Plan& pl, int mode, const PassParams& pp, const float* ws_base, cudaStream_t st) {
+    LaunchScope ls_(pass_class(mode), st);
+    if (pl.use_tc) return launch_pass_tc(pl, mode, pp, ws_base + pl.o_ua, ws_base + pl.o_wb, st);
+    return launch_pass(pl, mode, pp, st);
 }
 
 bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
@@ -192,6 +203,7 @@ int caps_set_tuning(const char* name, int value) {
         g_tune_spt = value;
         return 0;
     }
+    if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
         if (value < 0 || value > 64) return fail(CAPS_E_BADARG, "isplit must be in [0,64]");
         g_tune_isplit = value;
@@ -234,6 +246,13 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
         { LaunchScope ls_(kcLayout, st); k_prep_u<8><<<cdiv(n, 256), 256, 0, st>>>(u, ut, B, N, pl.nbt); }
         LAUNCH_CHECK();
     }
+    if (pl.use_tc) {
+        int rc;
+        { LaunchScope ls_(kcLayout, st); rc = launch_prep_u_tc(pl, u, w + pl.o_ua, st); }
+        if (rc) return rc;
+        { LaunchScope ls_(kcLayout, st); rc = launch_prep_w_tc(pl, W, w + pl.o_wb, st); }
+        if (rc) return rc;
+    }
     float* vsum = w + pl.o_vsum;
     float* part = w + pl.o_part;
     for (int r = 0; r < pl.Reff; ++r) {
@@ -245,17 +264,17 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
         int rc;
         if (r == 0) {
             pp.out = part;
-            { LaunchScope ls_(pass_class(kModeAUniform), st); rc = launch_pass(pl, kModeAUniform, pp, st); } if (rc) return rc;
+            if ((rc = run_pass(pl, kModeAUniform, pp, w, st))) return rc;
             if ((rc = launch_squash(pl, part, 1.f / (float)C, s_r, v_r, vsum, 0, last ? v : nullptr, st))) return rc;
         } else {
             float* c_r = w + pl.o_c + (pl.with_grad ? pl.cs * (r - 1) : 0);
             pp.X = vsum; pp.out = c_r;
-            { LaunchScope ls_(pass_class(kModeL), st); rc = launch_pass(pl, kModeL, pp, st); } if (rc) return rc;
+            if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
             const long n = (long)pl.nbt * N * 32;
             { LaunchScope ls_(kcSoftmax, st); k_softmax<<<cdiv(n, 128), 128, 0, st>>>(c_r, (last ? c_out : nullptr), B, N, C, pl.nbt); }
             LAUNCH_CHECK();
             pp.X = nullptr; pp.coef = c_r; pp.out = part;
-            { LaunchScope ls_(pass_class(kModeA), st); rc = launch_pass(pl, kModeA, pp, st); } if (rc) return rc;
+            if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
             if ((rc = launch_squash(pl, part, 1.f, s_r, v_r, vsum, 1, last ? v : nullptr, st))) return rc;
         }
     }
@@ -303,12 +322,12 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         PassParams pp{};
         pp.ut = ut; pp.W = Wp; pp.N = N; pp.C = C; pp.nbt = pl.nbt; pp.i_per_split = pl.i_per_split;
         pp.X = w + pl.o_ds + pl.xs * r; pp.out = tmp;                       // dc = u_hat . ds^r
-        { LaunchScope ls_(pass_class(kModeL), st); rc = launch_pass(pl, kModeL, pp, st); } if (rc) return rc;
+        if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
         const long n = (long)pl.nbt * N * 32;
         { LaunchScope ls_(kcSoftmax, st); k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt); }
         LAUNCH_CHECK();
         pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
-        { LaunchScope ls_(pass_class(kModeA), st); rc = launch_pass(pl, kModeA, pp, st); } if (rc) return rc;
+        if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
         if ((rc = launch_dsquash(pl, part, nullptr, nullptr, 0.f, nullptr, nullptr, w + pl.o_s + pl.xs * (r - 1),
                                  w + pl.o_ds + pl.xs * (r - 1), st)))
             return rc;
@@ -339,10 +358,19 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
 }
 
 int caps_margin_loss(const float* v, const int64_t* y, float scale, float* loss, float* scores_out,
-                     int B, int C, int D, void* stream) {
+                     float* scratch, int B, int C, int D, void* stream) {
     if (!v || !y || !loss || B < 0 || C <= 0 || D <= 0) return fail(CAPS_E_BADARG, "caps_margin_loss: bad argument");
-    { LaunchScope ls_(kcLoss, static_cast<cudaStream_t>(stream)); k_margin_loss<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(v, y, scale, loss, scores_out, B, C, D); }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long n = (long)B * C;
+    int blocks = scratch ? (int)((n + 1023) / 1024) : 1;        // ~4 (b,j) rows per thread
+    if (blocks > CAPS_MARGIN_SCRATCH_FLOATS) blocks = CAPS_MARGIN_SCRATCH_FLOATS;
+    if (blocks < 1) blocks = 1;
+    { LaunchScope ls_(kcLoss, st); k_margin_loss<<<blocks, 256, 0, st>>>(v, y, scale, loss, scratch, scores_out, B, C, D); }
     LAUNCH_CHECK();
+    if (blocks > 1) {
+        { LaunchScope ls_(kcLoss, st); k_margin_loss_final<<<1, 256, 0, st>>>(scratch, blocks, scale, loss); }
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -364,7 +392,7 @@ int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, 
 
 // ---- host-buffer step ------------------------------------------------------------------------
 namespace {
-struct HostStepLayout { size_t o_u, o_y, o_v, o_du, o_loss, o_ws, total; };
+struct HostStepLayout { size_t o_u, o_y, o_v, o_du, o_loss, o_lscr, o_ws, total; };
 bool host_step_layout(HostStepLayout& L, int B, int N, int C, int K, int D, int R) {
     const size_t wsb = caps_route_workspace_bytes(B, N, C, K, D, R, 1);
     if (wsb == 0) return false;
@@ -375,6 +403,7 @@ bool host_step_layout(HostStepLayout& L, int B, int N, int C, int K, int D, int 
     L.o_v = o; o += r256((size_t)B * C * D * 4);
     L.o_du = o; o += r256((size_t)B * N * K * 4);
     L.o_loss = o; o += 256;
+    L.o_lscr = o; o += r256(CAPS_MARGIN_SCRATCH_FLOATS * 4);
     L.o_ws = o; o += r256(wsb);
     L.total = o;
     return true;
@@ -408,7 +437,7 @@ int caps_route_step_host(const float* u_host, const int64_t* y_host, const float
     int rc;
     if ((rc = caps_route_forward(u_d, W_dev, v_d, nullptr, ws, wsb, B, N, C, K, D, R, 1, stream))) return rc;
     const float scale = 1.f / (float)B;
-    if ((rc = caps_margin_loss(v_d, y_d, scale, loss_d, nullptr, B, C, D, stream))) return rc;
+    if ((rc = caps_margin_loss(v_d, y_d, scale, loss_d, nullptr, reinterpret_cast<float*>(base + L.o_lscr), B, C, D, stream))) return rc;
     if ((rc = caps_route_backward(u_d, W_dev, nullptr, y_d, scale, nullptr, du_host ? du_d : nullptr, dW_dev, ws, wsb,
                                   B, N, C, K, D, R, stream)))
         return rc;

@@ -27,13 +27,19 @@ inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // are a pure function of the dims so forward and backward agree without any shared state.
 struct Plan {
     int B, N, C, K, D, R, Reff, DP, JW, JG, SPT, nbt, ntg, IS, i_per_split, M;
-    bool pad_w, with_grad;
+    bool pad_w, with_grad, use_tc;
     size_t xs, cs, us;                 // floats per X / coef / ut array
     // offsets (floats) into the workspace
-    size_t o_ut, o_wp, o_vsum, o_s, o_v, o_part, o_c, o_beta, o_tmp, o_ds, o_dupart, total;
+    size_t o_ua, o_wb, o_ut, o_wp, o_vsum, o_s, o_v, o_part, o_c, o_beta, o_tmp, o_ds, o_dupart, total;
 };
 
 int launch_pass(const Plan& pl, int mode, const PassParams& pp, cudaStream_t st);   // caps_pass.cu
 int launch_grad(const Plan& pl, const GradParams& gp, cudaStream_t st);             // caps_grad.cu
+// caps_pass_tc.cu: tcgen05 pass kernel (D == 16 only) and its operand preparation
+size_t tc_ua_floats(int B, int N);
+size_t tc_wb_floats(int N, int C);
+int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st);
+int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st);
+int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st);
 
 }  // namespace caps

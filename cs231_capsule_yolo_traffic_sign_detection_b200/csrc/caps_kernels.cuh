@@ -638,22 +638,40 @@ __global__ void k_reduce_du(const float* __restrict__ du_part, int JG, float* __
 // ---------------------------------------------------------------------------------------------
 // margin loss value, squash for the primary-capsule branch
 // ---------------------------------------------------------------------------------------------
-// one block, fixed-order tree: deterministic.  v public [B][C][D].
+// fixed-order two-level tree: deterministic.  v public [B][C][D].  With gridDim.x > 1 every
+// block writes its partial to part[blockIdx.x] and k_margin_loss_final adds them in order.
 static __global__ void k_margin_loss(const float* __restrict__ v, const int64_t* __restrict__ y, float scale,
-                              float* __restrict__ loss, float* __restrict__ scores, int B, int C, int D) {
-    __shared__ float red[1024];
+                                     float* __restrict__ loss, float* __restrict__ part,
+                                     float* __restrict__ scores, int B, int C, int D) {
+    __shared__ float red[256];
     float acc = 0.f;
     const long n = (long)B * C;
-    for (long e = threadIdx.x; e < n; e += blockDim.x) {
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
         const float* p = v + e * D;
         float m2 = 0.f;
         for (int d = 0; d < D; ++d) m2 = fmaf(p[d], p[d], m2);
-        const float m = sqrtf(m2);
+        const float m = sqrtf(m2);                           // reference models.py:117
         if (scores) scores[e] = m;
         const bool hit = (y[e / C] == (int64_t)(e % C));
         const float l = fmaxf(0.9f - m, 0.f), r = fmaxf(m - 0.1f, 0.f);
-        acc += hit ? l * l : 0.5f * r * r;
+        acc += hit ? l * l : 0.5f * r * r;                   // reference loss_fns.py:12-17
     }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (gridDim.x == 1) *loss = red[0] * scale;
+        else part[blockIdx.x] = red[0];
+    }
+}
+
+static __global__ void k_margin_loss_final(const float* __restrict__ part, int n, float scale, float* __restrict__ loss) {
+    __shared__ float red[256];
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) acc += part[e];
     red[threadIdx.x] = acc;
     __syncthreads();
     for (int s = blockDim.x / 2; s > 0; s >>= 1) {
@@ -699,9 +717,10 @@ static __global__ void k_fma_peak(float* __restrict__ sink, int iters, float m0,
         m[t] = m0 - 1e-6f * (float)(threadIdx.x + t);
         c[t] = c0 + 1e-7f * (float)(threadIdx.x * 3 + t);
     }
+#pragma unroll 4
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) a[t] = fmaf(a[t], m[t], c[t]);
+        for (int t = 0; t < 16; ++t) a[t] = fmaf(a[t], m[t & 3], c[(t >> 2) & 3]);
     }
     float s = 0.f;
 #pragma unroll

@@ -1,0 +1,356 @@
+// caps_pass_tc.cu -- tcgen05 / TMEM version of the pass kernel (sm_100a only).
+//
+// Same contract as k_pass in caps_kernels.cuh (modes A-uniform / A / L), but the K=8 prediction
+// contraction u_hat[b,i,j,:] = u[b,i,:] . W[i,j,:,:] runs on the 5th-gen tensor cores:
+//
+//   per input capsule i:   D[128 samples x (8 capsules x 16 dims)] = A_i[128 x 8] * B_i[128 x 8]^T
+//
+// as three kind::tf32 MMAs (3xTF32: lo*hi + hi*lo + hi*hi; measured 1e-7 relative error, i.e.
+// fp32-grade, tools/probe_tc.cu), accumulated in TMEM.  Operands are pre-split into tf32 hi/lo
+// halves and pre-arranged in the canonical no-swizzle K-major core-matrix layout by the prep
+// kernels below, so that one pipeline stage is two cp.async.bulk copies (8 KB of A, 8 KB of B).
+//
+// Warp roles (320 threads):  warps 0-7 epilogue, warp 8 bulk-copy producer, warp 9 MMA issuer.
+//   producer : waits smem_empty[s], arms smem_full[s] with expect_tx, issues the two bulk copies
+//   MMA      : waits smem_full[s] and tmem_empty[t], issues 3 tcgen05.mma, commits to
+//              smem_empty[s] (operands consumed) and tmem_full[t] (accumulator ready)
+//   epilogue : warp w reads TMEM lanes 32*(w%4).. (= its 32 samples) and the 64 columns of its 4
+//              capsules with one tcgen05.ld.32x32b.x64, releases tmem_empty[t], and does the
+//              per-sample part on the FMA pipe: acc += coef * u_hat (A modes) or
+//              out = u_hat . X (L mode).  lane <-> sample, exactly like the FFMA kernel.
+// Ring depths: 4 smem stages (64 KB), 4 TMEM accumulators (4 x 128 = all 512 columns).
+#include "caps_internal.h"
+
+namespace caps {
+namespace {
+
+constexpr int kTcStages = 4;          // smem ring
+constexpr int kTcAccum = 4;           // TMEM ring (4 x 128 columns)
+constexpr int kTcJW = 8;              // capsules per CTA  -> N = 128
+constexpr int kTcN = 128;
+constexpr int kTcABytes = 2 * 2 * 128 * 16;      // [hi/lo][kq][128 rows][16 B] = 8 KB
+constexpr int kTcBBytes = 2 * 2 * kTcN * 16;     // 8 KB
+constexpr int kTcStageBytes = kTcABytes + kTcBBytes;
+constexpr int kTcThreads = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Spin on try_wait; a wait that outlives ~4 s of SM clock is a protocol bug: trap instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor: no swizzle, K-major; LBO = byte distance between the two
+// 16-byte K chunks, SBO = byte distance between 8-row groups; version 1 (Blackwell).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 64 consecutive fp32 columns of this warp's 32 TMEM lanes -> 64 registers per thread
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+    hi = make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
+    lo = make_float4(tf32_rna(x.x - hi.x), tf32_rna(x.y - hi.y), tf32_rna(x.z - hi.z), tf32_rna(x.w - hi.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+// u [B][N][8] -> ua [ntq][N][hi/lo][kq][128 rows][4]  (row = sample within the 128-sample quad tile)
+__global__ void k_prep_u_tc(const float* __restrict__ u, float* __restrict__ ua, int B, int N, int ntq) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)ntq * N * 128) return;
+    const int r = (int)(idx & 127);
+    const long ti = idx >> 7;
+    const int i = (int)(ti % N);
+    const long tq = ti / N;
+    const long b = tq * 128 + r;
+    float* dst = ua + (size_t)ti * 2048 + r * 4;
+#pragma unroll
+    for (int kq = 0; kq < 2; ++kq) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+        if (b < B) x = ldg4(u + ((size_t)b * N + i) * 8 + kq * 4);
+        split4(x, hi, lo);
+        st4(dst + (0 * 2 + kq) * 512, hi);
+        st4(dst + (1 * 2 + kq) * 512, lo);
+    }
+}
+
+// W [N][C][8][16] -> wb [N][JG][hi/lo][kq][128 rows][4]  (row n = 16*(j - 8*jg) + d; 4 = k % 4)
+__global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb, int N, int C, int JG) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * JG * 128) return;
+    const int n = (int)(idx & 127);
+    const long ig = idx >> 7;
+    const int jg = (int)(ig % JG);
+    const long i = ig / JG;
+    const int j = jg * kTcJW + (n >> 4), d = n & 15;
+    float* dst = wb + (size_t)ig * 2048 + n * 4;
+#pragma unroll
+    for (int kq = 0; kq < 2; ++kq) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+        if (j < C) {
+            const float* src = W + (((size_t)i * C + j) * 8 + kq * 4) * 16 + d;
+            x = make_float4(__ldg(src), __ldg(src + 16), __ldg(src + 32), __ldg(src + 48));
+        }
+        split4(x, hi, lo);
+        st4(dst + (0 * 2 + kq) * 512, hi);
+        st4(dst + (1 * 2 + kq) * 512, lo);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+struct PassTcParams {
+    const float* ua;     // [ntq][N][2][2][128][4]
+    const float* wb;     // [N][JG][2][2][128][4]
+    const float* coef;   // kModeA: [nbt][N][C][32]
+    const float* X;      // kModeL: [nbt][C][4][32][4]
+    float* out;          // kModeL: [nbt][N][C][32];  kModeA*: part [IS][nbt][C][4][32][4]
+    int N, C, JG, nbt, i_per_split;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* stages = smem_raw;                                             // kTcStages x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kTcStages * kTcStageBytes);
+    uint64_t* smem_full = bars;                       // [kTcStages]
+    uint64_t* smem_empty = bars + kTcStages;          // [kTcStages]
+    uint64_t* tmem_full = bars + 2 * kTcStages;       // [kTcAccum]
+    uint64_t* tmem_empty = bars + 2 * kTcStages + kTcAccum;   // [kTcAccum]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2 * kTcAccum);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jg = blockIdx.y, tq = blockIdx.z;
+    const int i_begin = blockIdx.x * p.i_per_split;
+    const int i_end = min(p.N, i_begin + p.i_per_split);
+    const int n_i = max(i_end - i_begin, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&smem_full[s], 1); mbar_init(&smem_empty[s], 1); }
+        for (int t = 0; t < kTcAccum; ++t) { mbar_init(&tmem_full[t], 1); mbar_init(&tmem_empty[t], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 8) {
+        // ===== producer =====
+        if (lane == 0) {
+            for (int n = 0; n < n_i; ++n) {
+                const int s = n % kTcStages;
+                mbar_wait(&smem_empty[s], ((n / kTcStages) & 1) ^ 1);
+                mbar_expect_tx(&smem_full[s], kTcStageBytes);
+                const int i = i_begin + n;
+                uint8_t* dst = stages + s * kTcStageBytes;
+                bulk_g2s(dst, p.ua + ((size_t)tq * p.N + i) * 2048, kTcABytes, &smem_full[s]);
+                bulk_g2s(dst + kTcABytes, p.wb + ((size_t)i * p.JG + jg) * 2048, kTcBBytes, &smem_full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // kind::tf32, D = f32, A/B K-major, N = 128, M = 128
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int n = 0; n < n_i; ++n) {
+                const int s = n % kTcStages, t = n % kTcAccum;
+                mbar_wait(&tmem_empty[t], ((n / kTcAccum) & 1) ^ 1);
+                mbar_wait(&smem_full[s], (n / kTcStages) & 1);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(stages + s * kTcStageBytes), b0 = a0 + kTcABytes;
+                const uint64_t a_hi = umma_desc(a0, 2048, 128), a_lo = umma_desc(a0 + 4096, 2048, 128);
+                const uint64_t b_hi = umma_desc(b0, 2048, 128), b_lo = umma_desc(b0 + 4096, 2048, 128);
+                const uint32_t d = tmem_base + (uint32_t)(t * kTcN);
+                umma_tf32(d, a_lo, b_hi, idesc, 0);
+                umma_tf32(d, a_hi, b_lo, idesc, 1);
+                umma_tf32(d, a_hi, b_hi, idesc, 1);
+                umma_commit(&smem_empty[s]);          // operands of stage s consumed
+                umma_commit(&tmem_full[t]);           // accumulator t complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warp w -> samples of lane tile 4*tq + w%4, capsules j0 .. j0+3 =====
+        const int q = warp & 3, jh = warp >> 2;
+        const int tile = tq * 4 + q;
+        const bool tvalid = tile < p.nbt;
+        const int j0 = jg * kTcJW + jh * 4;
+        float acc[4][16];                 // A modes: running sums; L mode: the probe vectors X[b,j,:]
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int d = 0; d < 16; ++d) acc[jj][d] = 0.f;
+        if (MODE == kModeL && tvalid) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (j0 + jj < p.C) {
+#pragma unroll
+                    for (int dq = 0; dq < 4; ++dq) {
+                        const float4 x = ldg4(p.X + ((((size_t)tile * p.C + j0 + jj) * 4 + dq) * kLanes + lane) * 4);
+                        acc[jj][dq * 4 + 0] = x.x; acc[jj][dq * 4 + 1] = x.y; acc[jj][dq * 4 + 2] = x.z; acc[jj][dq * 4 + 3] = x.w;
+                    }
+                }
+        }
+        float cn[4] = {0.f, 0.f, 0.f, 0.f};
+        auto load_coef = [&](int i) {
+            if (MODE == kModeA && tvalid) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    cn[jj] = (j0 + jj < p.C) ? __ldg(p.coef + (((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane) : 0.f;
+            }
+        };
+        if (n_i > 0) load_coef(i_begin);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * 64);
+        for (int n = 0; n < n_i; ++n) {
+            const int t = n % kTcAccum;
+            const int i = i_begin + n;
+            float cc[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) cc[jj] = cn[jj];
+            if (n + 1 < n_i) load_coef(i + 1);
+            mbar_wait(&tmem_full[t], (n / kTcAccum) & 1);
+            tc_fence_after();
+            float uh[64];
+            tmem_ld64(lane_base + (uint32_t)(t * kTcN), uh);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[t]);      // accumulator t may be overwritten
+            if (MODE == kModeL) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float dot = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) dot = fmaf(uh[jj * 16 + d], acc[jj][d], dot);
+                    if (tvalid && j0 + jj < p.C) p.out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = dot;
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float f = (MODE == kModeA) ? cc[jj] : 1.f;
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) acc[jj][d] = fmaf(f, uh[jj * 16 + d], acc[jj][d]);
+                }
+            }
+        }
+        if (MODE != kModeL && tvalid) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+                if (j0 + jj < p.C) {
+#pragma unroll
+                    for (int dq = 0; dq < 4; ++dq)
+                        st4(p.out + (((((size_t)blockIdx.x * p.nbt + tile) * p.C + j0 + jj) * 4 + dq) * kLanes + lane) * 4,
+                            make_float4(acc[jj][dq * 4 + 0], acc[jj][dq * 4 + 1], acc[jj][dq * 4 + 2], acc[jj][dq * 4 + 3]));
+                }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+}  // namespace
+
+size_t tc_ua_floats(int B, int N) { return (size_t)cdiv(B > 0 ? B : 1, 128) * N * 2048; }
+size_t tc_wb_floats(int N, int C) { return (size_t)N * cdiv(C, kTcJW) * 2048; }
+
+int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st) {
+    const int ntq = cdiv(pl.B, 128);
+    const long nu = (long)ntq * pl.N * 128;
+    k_prep_u_tc<<<cdiv(nu, 256), 256, 0, st>>>(u, ua, pl.B, pl.N, ntq);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st) {
+    const int JG = cdiv(pl.C, kTcJW);
+    const long nw = (long)pl.N * JG * 128;
+    k_prep_w_tc<<<cdiv(nw, 256), 256, 0, st>>>(W, wb, pl.N, pl.C, JG);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st) {
+    PassTcParams tp{};
+    tp.ua = ua; tp.wb = wb; tp.coef = pp.coef; tp.X = pp.X; tp.out = pp.out;
+    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, kTcJW); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
+    const size_t smem = (size_t)kTcStages * kTcStageBytes + 256;
+    dim3 grid(pl.IS, tp.JG, cdiv(pl.nbt, 4)), block(kTcThreads);
+#define CAPS_LAUNCH_TC(MODE)                                                                             \
+    {                                                                                                    \
+        auto kern = k_pass_tc<MODE>;                                                                     \
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        kern<<<grid, block, smem, st>>>(tp);                                                             \
+    }
+    if (mode == kModeAUniform) CAPS_LAUNCH_TC(kModeAUniform)
+    else if (mode == kModeA) CAPS_LAUNCH_TC(kModeA)
+    else CAPS_LAUNCH_TC(kModeL)
+#undef CAPS_LAUNCH_TC
+    LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace caps

@@ -79,9 +79,12 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
 
 /* Margin loss value: sum_{b,j} [ T relu(0.9-m)^2 + 0.5 (1-T) relu(m-0.1)^2 ] * scale with
  * m = |v[b,j,:]|, T = (y[b]==j).  Replaces reference models.py:117 + loss_fns.py:12-17,23
- * (recon term off).  loss: one float (device).  scores_out: [B,C] or NULL. */
+ * (recon term off).  loss: one float (device).  scores_out: [B,C] or NULL.  scratch: device
+ * buffer of CAPS_MARGIN_SCRATCH_FLOATS floats for the two-level fixed-order reduction, or NULL
+ * (then one thread block does all the work: slow for large B, same result contract). */
+#define CAPS_MARGIN_SCRATCH_FLOATS 2048
 int caps_margin_loss(const float* v, const int64_t* y, float scale, float* loss,
-                     float* scores_out, int B, int C, int D, void* stream);
+                     float* scores_out, float* scratch, int B, int C, int D, void* stream);
 
 /* squash over the last dim of a [rows, D] array (reference models.py:64-67), any D >= 1.
  * Used by the primary-capsule branch (models.py:82).  y may alias x. */
@@ -114,6 +117,8 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
 /* Tuning knobs (process-wide, read at call time; defaults are chosen per shape).
  *   name = "spt"  samples per thread in the pass kernels (1, 2 or 4; 0 = auto)
  *   name = "isplit" forced number of splits of the N range (0 = auto)
+ *   name = "tc"   1 (default): tcgen05 tensor-core pass kernel where it applies (D == 16, C >= 4);
+ *                 0: fp32-FMA pass kernel everywhere
  *   name = "profile" 1: bracket every launch with CUDA events (see caps_profile_collect)
  * Returns 0, or CAPS_E_BADARG for an unknown name/value.  Meant for benchmarks and tests. */
 int caps_set_tuning(const char* name, int value);
