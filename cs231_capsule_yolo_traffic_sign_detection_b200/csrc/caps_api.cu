@@ -26,6 +26,7 @@ using namespace caps;
 
 int g_tune_spt = 0;      // 0 = auto
 int g_tune_isplit = 0;   // 0 = auto
+int g_tune_gradmma = 1;  // 1 = mma.sync gradient kernel where it applies (D == 16, C >= 7)
 int g_tune_tc = 1;       // 1 = use the tcgen05 pass kernel where it applies, 0 = FFMA kernel only
 
 // ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
@@ -203,6 +204,7 @@ int caps_set_tuning(const char* name, int value) {
         g_tune_spt = value;
         return 0;
     }
+    if (!strcmp(name, "gradmma")) { g_tune_gradmma = value != 0; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
         if (value < 0 || value > 64) return fail(CAPS_E_BADARG, "isplit must be in [0,64]");
@@ -271,7 +273,13 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
             pp.X = vsum; pp.out = c_r;
             if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
             const long n = (long)pl.nbt * N * 32;
-            { LaunchScope ls_(kcSoftmax, st); k_softmax<<<cdiv(n, 128), 128, 0, st>>>(c_r, (last ? c_out : nullptr), B, N, C, pl.nbt); }
+            {
+                LaunchScope ls_(kcSoftmax, st);
+                float* cp = last ? c_out : nullptr;
+                if (C <= 16) k_softmax_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
+                else if (C <= 48) k_softmax_reg<48><<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
+                else k_softmax<<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
+            }
             LAUNCH_CHECK();
             pp.X = nullptr; pp.coef = c_r; pp.out = part;
             if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
@@ -324,7 +332,12 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         pp.X = w + pl.o_ds + pl.xs * r; pp.out = tmp;                       // dc = u_hat . ds^r
         if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
         const long n = (long)pl.nbt * N * 32;
-        { LaunchScope ls_(kcSoftmax, st); k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt); }
+        {
+            LaunchScope ls_(kcSoftmax, st);
+            if (C <= 16) k_softmax_bwd_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+            else if (C <= 48) k_softmax_bwd_reg<48><<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+            else k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+        }
         LAUNCH_CHECK();
         pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
         if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
@@ -348,7 +361,11 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         gp.X[m] = w + pl.o_v + pl.xs * (r - 1);
         ++m;
     }
-    { LaunchScope ls_(kcGrad, st); rc = launch_grad(pl, gp, st); } if (rc) return rc;
+    {
+        LaunchScope ls_(kcGrad, st);
+        rc = (g_tune_gradmma && pl.DP == 16 && pl.D == 16 && pl.JW == 8) ? launch_grad_mma(pl, gp, st) : launch_grad(pl, gp, st);
+    }
+    if (rc) return rc;
     if (du != nullptr) {
         const long n = (long)pl.nbt * N * 32;
         { LaunchScope ls_(kcReduceDu, st); k_reduce_du<8><<<cdiv(n, 128), 128, 0, st>>>(gp.du_part, pl.JG, du, B, N, pl.nbt); }

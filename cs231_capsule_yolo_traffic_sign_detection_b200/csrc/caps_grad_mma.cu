@@ -1,0 +1,248 @@
+// caps_grad_mma.cu -- final backward pass with the two K=8 / D=16 contractions on tensor cores.
+//
+// Same contract as k_grad (caps_kernels.cuh):
+//     G_bij = sum_m alpha^m_bij X^m_bj          (fp32 FMA pipe, lane <-> sample, X in registers)
+//     dW_ij[k,d] = sum_b u_bi[k] G_bij[d]       (reduction over the batch)
+//     du_bi[k]   = sum_j sum_d W_ij[k,d] G_bij[d]
+// but the two contractions run as warp-level mma.sync.m16n8k8 TF32 with the 3xTF32 split
+// (lo*hi + hi*lo + hi*hi: fp32-grade accuracy), instead of 256 FFMA + a 124-shuffle transpose
+// reduction per (i, j, 32 samples).  The batch reduction of dW happens INSIDE the MMA (the MMA's
+// K dimension is the sample index), so there is no cross-lane reduction left at all.
+//
+// Why legacy mma.sync and not tcgen05 here: one side of both products is only 8 wide (k), and a
+// tcgen05.mma costs ~62 cycles whatever its N (tools/probe_tc.cu), so 8/16-column UMMAs would
+// waste the pipe; the G operand is produced per sample in registers, which is exactly the
+// register-fragment model of mma.sync.  (The u_hat passes, whose N is 128, use tcgen05.)
+//
+// One warp <-> one output capsule j; the CTA owns dW[i-tile][8 capsules] completely (it loops over
+// every 32-sample lane tile), so dW needs no atomics and is bit-reproducible.  Per (i, tile):
+//   1. every lane builds G[16] for its sample and parks G and u in a per-warp shared tile
+//   2. dW: 4 chunks of 8 samples:  C[d 16 x k 8] += A[d x b] * B[b x k]   (A = G^T, B = u)
+//   3. du: 2 x 16 samples, 2 K-steps: C[b 16 x k 8] += A[b x d] * B[d x k] (A = G, B = W^T, whose
+//      fragments are pre-split and pre-permuted in shared memory once per CTA)
+//   4. du fragments are summed across the 8 warps (capsules) through shared memory; one partial
+//      per j-group goes to global (k_reduce_du adds the j-groups in fixed order).
+#include "caps_internal.h"
+
+namespace caps {
+namespace {
+
+constexpr int kGmIT = 8;          // input capsules per CTA
+constexpr int kGmJW = 8;          // warps = output capsules per CTA
+constexpr int kGmDub = 4;         // capsules per du reduction round
+constexpr int kGmGStride = 24;    // floats per sample row of the G tile (bank-conflict-free fragment reads)
+
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// x = hi + lo with hi exactly representable in tf32; lo is passed as is (the MMA ignores its low
+// 13 mantissa bits, a 2^-22 relative effect).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// c += a * b with a (4 regs) and b (2 regs) given in fp32; 3xTF32
+__device__ __forceinline__ void mma3(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+    uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) split_tf32(a[t], ah[t], al[t]);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) split_tf32(b[t], bh[t], bl[t]);
+    mma_tf32_m16n8k8(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
+    mma_tf32_m16n8k8(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+    mma_tf32_m16n8k8(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+}
+
+// grid = (ceil(N/8), ceil(C/8)); block = 256.  K = 8, D = 16 only.
+template <int M>
+__global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
+    constexpr int IT = kGmIT, JW = kGmJW, DUB = kGmDub, GS = kGmGStride, NT = 32 * JW;
+    extern __shared__ __align__(16) float smem[];
+    float* Wfrag = smem;                                   // [IT][JW][ks 2][hl 2][32 lanes][2]
+    float* dWsm = Wfrag + IT * JW * 256;                   // [IT][JW][32 lanes][4]
+    float* Gs = dWsm + IT * JW * 128;                      // [JW][32][GS]
+    float* Us = Gs + JW * 32 * GS;                         // [JW][32][8]
+    float* dusm = Us + JW * 32 * 8;                        // [JW][DUB][32 lanes][8]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
+    const int i0 = blockIdx.x * IT;
+    const int ni = min(IT, p.N - i0);
+    const int j0 = blockIdx.y * JW;
+    const int j = j0 + warp;
+    const bool jvalid = j < p.C;
+    const int njv = min(JW, p.C - j0);
+
+    // W^T fragments for du:  B[d][k] = W[k][d];  b0 = (d = t + 8 ks, k = g), b1 = (d = t + 4 + 8 ks, k = g)
+    for (int e = threadIdx.x; e < IT * JW * 64; e += NT) {
+        const int l = e & 31, ks = (e >> 5) & 1, w = (e >> 6) % JW, il = e / (64 * JW);
+        const int gg = l >> 2, tt = l & 3;
+        float w0 = 0.f, w1 = 0.f;
+        if (il < ni && w < njv) {
+            const float* row = p.W + ((size_t)(i0 + il) * p.C + j0 + w) * 128 + gg * 16;      // W[i][j][k = gg][:]
+            w0 = __ldg(row + tt + 8 * ks);
+            w1 = __ldg(row + tt + 4 + 8 * ks);
+        }
+        uint32_t h0, l0, h1, l1;
+        split_tf32(w0, h0, l0);
+        split_tf32(w1, h1, l1);
+        float* dst = Wfrag + (size_t)((il * JW + w) * 2 + ks) * 128;
+        *reinterpret_cast<float2*>(dst + l * 2) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
+        *reinterpret_cast<float2*>(dst + 64 + l * 2) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+    }
+    for (int e = threadIdx.x; e < IT * JW * 128; e += NT) dWsm[e] = 0.f;
+    __syncthreads();
+
+    float* Gw = Gs + warp * 32 * GS;
+    float* Uw = Us + warp * 32 * 8;
+
+    for (int tile = 0; tile < p.nbt; ++tile) {
+        float xr[M][16];
+        if (jvalid) {
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int dq = 0; dq < 4; ++dq) {
+                    const float4 x = ldg4(p.X[m] + ((((size_t)tile * p.C + j) * 4 + dq) * kLanes + lane) * 4);
+                    xr[m][dq * 4 + 0] = x.x; xr[m][dq * 4 + 1] = x.y; xr[m][dq * 4 + 2] = x.z; xr[m][dq * 4 + 3] = x.w;
+                }
+        }
+        for (int ib = 0; ib < IT; ib += DUB) {
+#pragma unroll 1
+            for (int ii = 0; ii < DUB; ++ii) {
+                const int il = ib + ii;
+                float duf[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) duf[e] = 0.f;
+                if (jvalid && il < ni) {
+                    const int i = i0 + il;
+                    const float4 u0 = ldg4(p.ut + ((((size_t)tile * p.N + i) * 2 + 0) * kLanes + lane) * 4);
+                    const float4 u1 = ldg4(p.ut + ((((size_t)tile * p.N + i) * 2 + 1) * kLanes + lane) * 4);
+                    float G[16];
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) G[d] = 0.f;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float al = p.coef[m] != nullptr
+                                             ? __ldg(p.coef[m] + (((size_t)tile * p.N + i) * p.C + j) * kLanes + lane)
+                                             : p.cconst[m];
+#pragma unroll
+                        for (int d = 0; d < 16; ++d) G[d] = fmaf(al, xr[m][d], G[d]);
+                    }
+                    __syncwarp();                                   // previous round's fragment reads are done
+#pragma unroll
+                    for (int dq = 0; dq < 4; ++dq)
+                        st4(Gw + lane * GS + dq * 4, make_float4(G[dq * 4], G[dq * 4 + 1], G[dq * 4 + 2], G[dq * 4 + 3]));
+                    st4(Uw + lane * 8, u0);
+                    st4(Uw + lane * 8 + 4, u1);
+                    __syncwarp();
+                    // ---- dW[d][k] += sum_b G[b][d] u[b][k] : 4 chunks of 8 samples, two accumulators
+                    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float* gr0 = Gw + (8 * c + t) * GS;
+                        const float* gr1 = Gw + (8 * c + t + 4) * GS;
+                        const float a[4] = {gr0[g], gr0[g + 8], gr1[g], gr1[g + 8]};
+                        const float b[2] = {Uw[(8 * c + t) * 8 + g], Uw[(8 * c + t + 4) * 8 + g]};
+                        if (c & 1) mma3(c1, a, b); else mma3(c0, a, b);
+                    }
+                    float* dw = dWsm + (size_t)((il * JW + warp) * 32 + lane) * 4;     // lane-private: no hazard
+                    float4 acc = *reinterpret_cast<float4*>(dw);
+                    acc.x += c0[0] + c1[0]; acc.y += c0[1] + c1[1]; acc.z += c0[2] + c1[2]; acc.w += c0[3] + c1[3];
+                    *reinterpret_cast<float4*>(dw) = acc;
+                    // ---- du[b][k] = sum_d G[b][d] W[k][d] : 2 x 16 samples, 2 K-steps of 8 dims
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        float cc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const float* gr0 = Gw + (16 * mt + g) * GS + 8 * ks;
+                            const float* gr1 = Gw + (16 * mt + g + 8) * GS + 8 * ks;
+                            uint32_t ah[4], al[4];
+                            split_tf32(gr0[t], ah[0], al[0]);
+                            split_tf32(gr1[t], ah[1], al[1]);
+                            split_tf32(gr0[t + 4], ah[2], al[2]);
+                            split_tf32(gr1[t + 4], ah[3], al[3]);
+                            const float* wf = Wfrag + (size_t)((il * JW + warp) * 2 + ks) * 128;
+                            const float2 bh = *reinterpret_cast<const float2*>(wf + lane * 2);
+                            const float2 bl = *reinterpret_cast<const float2*>(wf + 64 + lane * 2);
+                            mma_tf32_m16n8k8(cc, al[0], al[1], al[2], al[3], __float_as_uint(bh.x), __float_as_uint(bh.y));
+                            mma_tf32_m16n8k8(cc, ah[0], ah[1], ah[2], ah[3], __float_as_uint(bl.x), __float_as_uint(bl.y));
+                            mma_tf32_m16n8k8(cc, ah[0], ah[1], ah[2], ah[3], __float_as_uint(bh.x), __float_as_uint(bh.y));
+                        }
+                        duf[mt * 4 + 0] = cc[0]; duf[mt * 4 + 1] = cc[1]; duf[mt * 4 + 2] = cc[2]; duf[mt * 4 + 3] = cc[3];
+                    }
+                }
+                float* ds = dusm + (size_t)((warp * DUB + ii) * 32 + lane) * 8;
+                st4(ds, make_float4(duf[0], duf[1], duf[2], duf[3]));
+                st4(ds + 4, make_float4(duf[4], duf[5], duf[6], duf[7]));
+            }
+            __syncthreads();
+            // sum the 8 capsules' du fragments; thread <-> (ii, lane, half)
+            for (int e = threadIdx.x; e < DUB * 64; e += NT) {
+                const int half = e & 1, l = (e >> 1) & 31, ii = e >> 6;
+                const int il = ib + ii;
+                if (il < ni) {
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < JW; ++w) {
+                        const float4 x = *reinterpret_cast<const float4*>(dusm + (size_t)((w * DUB + ii) * 32 + l) * 8 + half * 4);
+                        sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+                    }
+                    // fragment (mt = half): c0 (b = 16mt+gg, k = 2tt), c1 (.., k = 2tt+1), c2 (b + 8, k = 2tt), c3 (b + 8, 2tt+1)
+                    const int gg = l >> 2, tt = l & 3, b0 = 16 * half + gg;
+                    const int kq = (2 * tt) >> 2, kk = (2 * tt) & 3;
+                    float* dst = p.du_part + ((((size_t)blockIdx.y * p.nbt + tile) * p.N + i0 + il) * 2 + kq) * kLanes * 4;
+                    *reinterpret_cast<float2*>(dst + b0 * 4 + kk) = make_float2(sum.x, sum.y);
+                    *reinterpret_cast<float2*>(dst + (b0 + 8) * 4 + kk) = make_float2(sum.z, sum.w);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // dW fragments -> public [N][C][8][16]:  c0 (d = g, k = 2t), c1 (d = g, k = 2t+1), c2 (d = g+8, k = 2t), c3 (d = g+8, k = 2t+1)
+    for (int e = threadIdx.x; e < IT * JW * 32; e += NT) {
+        const int l = e & 31, w = (e >> 5) % JW, il = e / (32 * JW);
+        if (il < ni && w < njv) {
+            const float4 v = *reinterpret_cast<const float4*>(dWsm + (size_t)e * 4);
+            const int gg = l >> 2, tt = l & 3;
+            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j0 + w) * 128;
+            dst[(2 * tt) * 16 + gg] = v.x;
+            dst[(2 * tt + 1) * 16 + gg] = v.y;
+            dst[(2 * tt) * 16 + gg + 8] = v.z;
+            dst[(2 * tt + 1) * 16 + gg + 8] = v.w;
+        }
+    }
+}
+
+template <int M>
+int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
+    const size_t smem = ((size_t)kGmIT * kGmJW * 256 + kGmIT * kGmJW * 128 + kGmJW * 32 * kGmGStride + kGmJW * 32 * 8 +
+                         kGmJW * kGmDub * 32 * 8) * sizeof(float);
+    auto kern = k_grad_mma<M>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, kGmJW)), block(32 * kGmJW);
+    kern<<<grid, block, smem, st>>>(gp);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// D == 16, K == 8, 8 capsules per CTA (Plan::JW == 8), R <= 5
+int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {
+    switch (pl.M) {
+        case 1: return launch_t<1>(pl, gp, st);
+        case 3: return launch_t<3>(pl, gp, st);
+        case 5: return launch_t<5>(pl, gp, st);
+        case 7: return launch_t<7>(pl, gp, st);
+        case 9: return launch_t<9>(pl, gp, st);
+    }
+    return fail(CAPS_E_UNSUPPORTED, "R=%d unsupported", pl.R);
+}
+
+}  // namespace caps

@@ -35,6 +35,7 @@ struct Plan {
 
 int launch_pass(const Plan& pl, int mode, const PassParams& pp, cudaStream_t st);   // caps_pass.cu
 int launch_grad(const Plan& pl, const GradParams& gp, cudaStream_t st);             // caps_grad.cu
+int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st);         // caps_grad_mma.cu (D == 16, JW == 8)
 // caps_pass_tc.cu: tcgen05 pass kernel (D == 16 only) and its operand preparation
 size_t tc_ua_floats(int B, int N);
 size_t tc_wb_floats(int N, int C);

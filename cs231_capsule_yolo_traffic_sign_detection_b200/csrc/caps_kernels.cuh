@@ -442,6 +442,65 @@ static __global__ void k_softmax_bwd(const float* __restrict__ c, const float* _
     }
 }
 
+// register-resident variants for C <= CMAX: one read + one write of the [.,C] row per thread
+template <int CMAX>
+__global__ void k_softmax_reg(float* __restrict__ coef, float* __restrict__ c_pub, int B, int N, int C, int nbt) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)nbt * N * kLanes) return;
+    const int lane = (int)(idx & 31);
+    const long ti = idx >> 5;
+    float* p = coef + (size_t)ti * C * kLanes + lane;
+    float v[CMAX];
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j) v[j] = j < C ? p[(size_t)j * kLanes] : -INFINITY;
+    float mx = v[0];
+#pragma unroll
+    for (int j = 1; j < CMAX; ++j) mx = fmaxf(mx, v[j]);
+    float z = 0.f;
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j) {
+        v[j] = j < C ? expf(v[j] - mx) : 0.f;
+        z += v[j];
+    }
+    const long b = (ti / N) * kLanes + lane;
+    const int i = (int)(ti % N);
+    float* pub = (c_pub != nullptr && b < B) ? c_pub + ((size_t)b * N + i) * C : nullptr;
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j)
+        if (j < C) {
+            const float c = v[j] / z;
+            p[(size_t)j * kLanes] = c;
+            if (pub) pub[j] = c;
+        }
+}
+
+template <int CMAX>
+__global__ void k_softmax_bwd_reg(const float* __restrict__ c, const float* __restrict__ dc,
+                                  const float* __restrict__ beta_prev, float* __restrict__ beta_out,
+                                  int N, int C, int nbt) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)nbt * N * kLanes) return;
+    const int lane = (int)(idx & 31);
+    const size_t o = (size_t)(idx >> 5) * C * kLanes + lane;
+    float cv[CMAX], dv[CMAX];
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j) {
+        cv[j] = j < C ? c[o + (size_t)j * kLanes] : 0.f;
+        dv[j] = j < C ? dc[o + (size_t)j * kLanes] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j) t = fmaf(cv[j], dv[j], t);
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j)
+        if (j < C) {
+            const size_t q = o + (size_t)j * kLanes;
+            float bnew = cv[j] * (dv[j] - t);
+            if (beta_prev != nullptr) bnew += beta_prev[q];
+            beta_out[q] = bnew;
+        }
+}
+
 static __global__ void k_fill(float* __restrict__ p, float val, long n) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < n) p[idx] = val;

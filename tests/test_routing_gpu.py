@@ -147,6 +147,30 @@ def test_bit_reproducible_and_tuning_invariant(capsb):
         capsb._cabi.set_tuning('isplit', 0)
 
 
+def test_tensor_core_and_fma_engines_agree(capsb):
+    """The tcgen05 pass kernel / mma.sync gradient kernel (3xTF32) and the plain fp32-FMA kernels are
+    two implementations of the same contract; both must sit inside the oracle's tolerance and
+    agree with each other to fp32 round-off."""
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = 200, 160, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=21)
+    ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R)
+    res = {}
+    try:
+        for name, tc, gm in (('tensor', 1, 1), ('fma', 0, 0), ('mixed', 1, 0)):
+            capsb._cabi.set_tuning('tc', tc)
+            capsb._cabi.set_tuning('gradmma', gm)
+            res[name] = cuda_step(capsb, u, W, y, R)
+            for k, tol in (('v', TOL_V), ('c', TOL_V), ('du', TOL_G), ('dW', TOL_G)):
+                assert rel_err(res[name][k], ref[k]) < tol, (name, k)
+    finally:
+        capsb._cabi.set_tuning('tc', 1)
+        capsb._cabi.set_tuning('gradmma', 1)
+    for k in ('v', 'c', 'du', 'dW'):
+        assert rel_err(res['tensor'][k], res['fma'][k]) < 5e-6, k
+
+
 def test_batch_permutation_and_additivity_at_full_size(capsb):
     """Size-independent properties at BASELINE.json's shape (1152 -> 43x16, R=3), where the
     oracle is too slow: samples are independent, so (a) permuting the batch permutes v and du

@@ -56,7 +56,9 @@ constexpr int M = 128, NMAX = 256;
 
 // A: [128][8] row-major fp32, B: [N][8] row-major fp32 (B^T of the math).  D: [128][N].
 // split=0: plain tf32 (hardware truncates);  split=1: 3xTF32.
-__global__ void __launch_bounds__(128, 1) k_check(const float* A, const float* B, float* D, int N, int split, int reps, long long* cycles) {
+// amajor=1: A is stored MN-major: [m/4][k][m%4] (8 k-rows x 16 bytes per 4-row quad; SBO = 128 B between quads)
+__global__ void __launch_bounds__(128, 1) k_check(const float* A, const float* B, float* D, int N, int split, int reps, long long* cycles,
+                                                  int amajor = 0, int Mrows = 128) {
     __shared__ __align__(1024) float sA[2][2 * M * 4];     // [hi/lo][kq][row][4]
     __shared__ __align__(1024) float sB[2][2 * NMAX * 4];
     __shared__ __align__(8) uint64_t bar;
@@ -65,8 +67,9 @@ __global__ void __launch_bounds__(128, 1) k_check(const float* A, const float* B
     for (int e = tid; e < M * 8; e += 128) {
         const int r = e / 8, k = e % 8;
         const float x = A[e], hi = split ? tf32_rna(x) : x, lo = split ? tf32_rna(x - hi) : 0.f;
-        sA[0][(k / 4) * M * 4 + r * 4 + (k % 4)] = hi;
-        sA[1][(k / 4) * M * 4 + r * 4 + (k % 4)] = lo;
+        const int off = amajor ? (r / 4) * 32 + k * 4 + (r % 4) : (k / 4) * M * 4 + r * 4 + (k % 4);
+        sA[0][off] = hi;
+        sA[1][off] = lo;
     }
     for (int e = tid; e < N * 8; e += 128) {
         const int r = e / 8, k = e % 8;
@@ -85,10 +88,11 @@ __global__ void __launch_bounds__(128, 1) k_check(const float* A, const float* B
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)amajor << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(Mrows >> 4) << 24);
     long long t0 = 0, t1 = 0;
     if (tid == 0) {
-        const uint64_t a_hi = make_desc(smem_u32(sA[0]), M * 16, 128), a_lo = make_desc(smem_u32(sA[1]), M * 16, 128);
+        const uint64_t a_hi = amajor ? make_desc(smem_u32(sA[0]), 4096, 128) : make_desc(smem_u32(sA[0]), M * 16, 128);
+        const uint64_t a_lo = amajor ? make_desc(smem_u32(sA[1]), 4096, 128) : make_desc(smem_u32(sA[1]), M * 16, 128);
         const uint64_t b_hi = make_desc(smem_u32(sB[0]), N * 16, 128), b_lo = make_desc(smem_u32(sB[1]), N * 16, 128);
         t0 = clock64();
         for (int r = 0; r < reps; ++r) {
@@ -177,6 +181,44 @@ int main() {
             printf("check N=%3d split=%d: max abs err %.3e (max |ref| %.3e, rel %.3e) %s\n", N, split, maxerr, maxref,
                    maxerr / maxref, maxerr / maxref < (split ? 2e-6 : 3e-3) ? "OK" : "FAIL");
         }
+    }
+    // MN-major A (the layout the gradient kernel wants for G^T), M = 128 and M = 64
+    for (int Mr : {128, 64}) for (int N : {16, 8}) {
+        if (Mr == 128 && N == 8) continue;
+        cudaMemset(dD, 0, M * NMAX * 4);
+        k_check<<<1, 128>>>(dA, dB, dD, N, 1, 1, dC, 1, Mr);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("MN-major M=%d N=%d: CUDA error %s\n", Mr, N, cudaGetErrorString(e)); return 1; }
+        std::vector<float> hD(M * N);
+        cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
+        // M=64: rows 0..63 of D live in TMEM lanes 0..31 and 64..95?  print the row map we observe
+        double maxerr = 0, maxref = 0; int bad = 0;
+        for (int r = 0; r < Mr; ++r)
+            for (int n = 0; n < N; ++n) {
+                double ref = 0;
+                for (int k = 0; k < 8; ++k) ref += (double)hA[r * 8 + k] * (double)hB[n * 8 + k];
+                double err = fabs(ref - hD[r * N + n]);
+                if (err > 1e-5) ++bad;
+                maxerr = fmax(maxerr, err); maxref = fmax(maxref, fabs(ref));
+            }
+        printf("check MN-major A, M=%3d N=%2d: max abs err %.3e rel %.3e bad %d %s\n", Mr, N, maxerr, maxerr / maxref, bad,
+               maxerr / maxref < 2e-6 ? "OK" : "FAIL(lane map?)");
+        if (Mr == 64 && bad) {
+            // find which TMEM lane holds math row r (compare column 0)
+            for (int r = 0; r < 64; r += 9) {
+                double ref = 0; for (int k = 0; k < 8; ++k) ref += (double)hA[r * 8 + k] * (double)hB[0 * 8 + k];
+                for (int l = 0; l < 128; ++l) if (fabs(hD[l * N] - ref) < 1e-6) printf("   math row %d found in TMEM lane %d\n", r, l);
+            }
+        }
+    }
+    for (int cfg = 0; cfg < 4; ++cfg) {
+        const int Ns[4] = {16, 8, 16, 32}, Ms[4] = {128, 64, 64, 128};
+        long long hc[2];
+        const int reps = 2000;
+        k_check<<<1, 128>>>(dA, dB, dD, Ns[cfg], 1, reps, dC, 0, Ms[cfg]);
+        cudaDeviceSynchronize();
+        cudaMemcpy(hc, dC, 16, cudaMemcpyDeviceToHost);
+        printf("issue rate M=%d N=%d: %.1f cycles per MMA\n", Ms[cfg], Ns[cfg], (double)hc[0] / (3.0 * reps));
     }
     for (int N : {128, 256}) {
         long long hc[2];
