@@ -175,6 +175,9 @@ def main_gpu(args, rank, world, device):
         _cabi.set_tuning('spt', args.spt)
     if args.isplit:
         _cabi.set_tuning('isplit', args.isplit)
+    for kv in filter(None, args.tune.split(',')):
+        k, val = kv.split('=')
+        _cabi.set_tuning(k, int(val))
     torch.manual_seed(1234 + rank)
     g = torch.Generator(device='cpu').manual_seed(1234 + rank)
 
@@ -331,6 +334,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--spt', type=int, default=0)
     ap.add_argument('--isplit', type=int, default=0)
+    ap.add_argument('--tune', default='', help='comma list name=value passed to caps_set_tuning')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 

@@ -38,22 +38,25 @@ __device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], uint32_t a0, uin
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// x = hi + lo with hi exactly representable in tf32; lo is passed as is (the MMA ignores its low
-// 13 mantissa bits, a 2^-22 relative effect).
+// 3xTF32 split.  The tensor core reads only the top 19 bits of an operand (it truncates), so the
+// "hi" half of x is x itself; lo = x - trunc(x) is exact in fp32 and costs one LOP3 + one FADD
+// (cvt.rna.tf32 is a 5-instruction sequence in SASS).  Dropped terms (lo*lo and the truncation of
+// lo) are ~2^-20 relative.
+__device__ __forceinline__ uint32_t tf32_lo(float x) {
+    return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+// used once per CTA for the W fragments (round-to-nearest hi, exact lo)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // c += a * b with a (4 regs) and b (2 regs) given in fp32; 3xTF32
 __device__ __forceinline__ void mma3(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
-    uint32_t ah[4], al[4], bh[2], bl[2];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) split_tf32(a[t], ah[t], al[t]);
-#pragma unroll
-    for (int t = 0; t < 2; ++t) split_tf32(b[t], bh[t], bl[t]);
-    mma_tf32_m16n8k8(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
-    mma_tf32_m16n8k8(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
-    mma_tf32_m16n8k8(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+    const uint32_t a0 = __float_as_uint(a[0]), a1 = __float_as_uint(a[1]), a2 = __float_as_uint(a[2]), a3 = __float_as_uint(a[3]);
+    const uint32_t b0 = __float_as_uint(b[0]), b1 = __float_as_uint(b[1]);
+    mma_tf32_m16n8k8(c, tf32_lo(a[0]), tf32_lo(a[1]), tf32_lo(a[2]), tf32_lo(a[3]), b0, b1);
+    mma_tf32_m16n8k8(c, a0, a1, a2, a3, tf32_lo(b[0]), tf32_lo(b[1]));
+    mma_tf32_m16n8k8(c, a0, a1, a2, a3, b0, b1);
 }
 
 // grid = (ceil(N/8), ceil(C/8)); block = 256.  K = 8, D = 16 only.
@@ -99,6 +102,29 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
     float* Gw = Gs + warp * 32 * GS;
     float* Uw = Us + warp * 32 * 8;
 
+    // per-(b,i) operands of the NEXT unit are fetched while the current one computes (8 warps per
+    // SM cannot hide a ~1000-cycle global load by themselves)
+    float4 un0 = make_float4(0.f, 0.f, 0.f, 0.f), un1 = un0;
+    float aln[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) aln[m] = 0.f;
+    const float* coefp[M];
+    float cconst[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { coefp[m] = p.coef[m]; cconst[m] = p.cconst[m]; }
+    const float* utp = p.ut;
+    const size_t cstride = (size_t)p.C * kLanes;           // coef elements between consecutive i
+    auto load_unit = [&](int tile, int il) {
+        const size_t ti = (size_t)tile * p.N + i0 + il;
+        const float* up = utp + ti * (2 * kLanes * 4) + lane * 4;
+        un0 = ldg4(up);
+        un1 = ldg4(up + kLanes * 4);
+        const size_t co = ti * cstride + (size_t)j * kLanes + lane;
+#pragma unroll
+        for (int m = 0; m < M; ++m) aln[m] = coefp[m] != nullptr ? __ldg(coefp[m] + co) : cconst[m];
+    };
+    if (jvalid && p.nbt > 0) load_unit(0, 0);
+
     for (int tile = 0; tile < p.nbt; ++tile) {
         float xr[M][16];
         if (jvalid) {
@@ -118,20 +144,18 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) duf[e] = 0.f;
                 if (jvalid && il < ni) {
-                    const int i = i0 + il;
-                    const float4 u0 = ldg4(p.ut + ((((size_t)tile * p.N + i) * 2 + 0) * kLanes + lane) * 4);
-                    const float4 u1 = ldg4(p.ut + ((((size_t)tile * p.N + i) * 2 + 1) * kLanes + lane) * 4);
+                    const float4 u0 = un0, u1 = un1;
                     float G[16];
 #pragma unroll
                     for (int d = 0; d < 16; ++d) G[d] = 0.f;
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        const float al = p.coef[m] != nullptr
-                                             ? __ldg(p.coef[m] + (((size_t)tile * p.N + i) * p.C + j) * kLanes + lane)
-                                             : p.cconst[m];
+                        const float al = aln[m];
 #pragma unroll
                         for (int d = 0; d < 16; ++d) G[d] = fmaf(al, xr[m][d], G[d]);
                     }
+                    if (il + 1 < ni) load_unit(tile, il + 1);
+                    else if (tile + 1 < p.nbt) load_unit(tile + 1, 0);
                     __syncwarp();                                   // previous round's fragment reads are done
 #pragma unroll
                     for (int dq = 0; dq < 4; ++dq)
@@ -161,11 +185,10 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
                         for (int ks = 0; ks < 2; ++ks) {
                             const float* gr0 = Gw + (16 * mt + g) * GS + 8 * ks;
                             const float* gr1 = Gw + (16 * mt + g + 8) * GS + 8 * ks;
+                            const float av[4] = {gr0[t], gr1[t], gr0[t + 4], gr1[t + 4]};
                             uint32_t ah[4], al[4];
-                            split_tf32(gr0[t], ah[0], al[0]);
-                            split_tf32(gr1[t], ah[1], al[1]);
-                            split_tf32(gr0[t + 4], ah[2], al[2]);
-                            split_tf32(gr1[t + 4], ah[3], al[3]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { ah[e] = __float_as_uint(av[e]); al[e] = tf32_lo(av[e]); }
                             const float* wf = Wfrag + (size_t)((il * JW + warp) * 2 + ks) * 128;
                             const float2 bh = *reinterpret_cast<const float2*>(wf + lane * 2);
                             const float2 bl = *reinterpret_cast<const float2*>(wf + 64 + lane * 2);

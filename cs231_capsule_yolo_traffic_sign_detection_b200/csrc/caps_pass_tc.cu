@@ -18,58 +18,80 @@
 //              capsules with one tcgen05.ld.32x32b.x64, releases tmem_empty[t], and does the
 //              per-sample part on the FMA pipe: acc += coef * u_hat (A modes) or
 //              out = u_hat . X (L mode).  lane <-> sample, exactly like the FFMA kernel.
-// Ring depths: 4 smem stages (64 KB), 4 TMEM accumulators (4 x 128 = all 512 columns).
+// Ring depths: `ns` smem stages (default 10 = 160 KB: the bulk copies have ~2000 cycles of latency to
+// cover at ~250 cycles per stage), 4 TMEM accumulators (4 x 128 = all 512 columns).
 #include "caps_internal.h"
 
 namespace caps {
 namespace {
 
-constexpr int kTcStages = 4;          // smem ring
-constexpr int kTcAccum = 4;           // TMEM ring (4 x 128 columns)
+constexpr int kTcMaxStages = 12;      // smem ring depth is a launch parameter (<= 12 x 16 KB)
+constexpr int kTcAccum = 4;           // TMEM ring (4 x 128 columns); power of two (index = n & 3, phase = (n >> 2) & 1)
 constexpr int kTcJW = 8;              // capsules per CTA  -> N = 128
 constexpr int kTcN = 128;
 constexpr int kTcABytes = 2 * 2 * 128 * 16;      // [hi/lo][kq][128 rows][16 B] = 8 KB
 constexpr int kTcBBytes = 2 * 2 * kTcN * 16;     // 8 KB
-constexpr int kTcStageBytes = kTcABytes + kTcBBytes;
+constexpr int kTcOperandBytes = kTcABytes + kTcBBytes;       // 16 KB of MMA operands per stage
+constexpr int kTcCoefBytes = 4 * kTcJW * 32 * 4;              // kModeA: [4 lane tiles][8 capsules][32 lanes] coefficients
+__host__ __device__ constexpr int tc_stage_bytes(int mode) { return kTcOperandBytes + (mode == kModeA ? kTcCoefBytes : 0); }
 constexpr int kTcThreads = 320;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// all barrier helpers take 32-bit shared-window addresses computed once per thread
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 // Spin on try_wait; a wait that outlives ~4 s of SM clock is a protocol bug: trap instead of hanging.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
+// The clock is only read on the slow path.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
-    for (;;) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) break;
+    while (!mbar_try(bar, parity))
         if (clock64() - t0 > 8000000000LL) __trap();
-    }
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 // shared-memory matrix descriptor: no swizzle, K-major; LBO = byte distance between the two
 // 16-byte K chunks, SBO = byte distance between 8-row groups; version 1 (Blackwell).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// One pipeline stage of tensor work, issued by ONE elected lane of a converged warp:
+//   D  = a_lo*b_hi ;  D += a_hi*b_lo ;  D += a_hi*b_hi        (3xTF32)
+// then two commits: bar_smem (operands consumed) and bar_tmem (accumulator complete).
+__device__ __forceinline__ void umma_stage(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                           uint32_t idesc, uint32_t bar_smem, uint32_t bar_tmem) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pf, pt;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.ne.b32 pf, 0, 0;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, pf;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_smem), "r"(bar_tmem)
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -159,19 +181,22 @@ struct PassTcParams {
     const float* coef;   // kModeA: [nbt][N][C][32]
     const float* X;      // kModeL: [nbt][C][4][32][4]
     float* out;          // kModeL: [nbt][N][C][32];  kModeA*: part [IS][nbt][C][4][32][4]
-    int N, C, JG, nbt, i_per_split;
+    int N, C, JG, nbt, i_per_split, ns;
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* stages = smem_raw;                                             // kTcStages x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kTcStages * kTcStageBytes);
-    uint64_t* smem_full = bars;                       // [kTcStages]
-    uint64_t* smem_empty = bars + kTcStages;          // [kTcStages]
-    uint64_t* tmem_full = bars + 2 * kTcStages;       // [kTcAccum]
-    uint64_t* tmem_empty = bars + 2 * kTcStages + kTcAccum;   // [kTcAccum]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 2 * kTcAccum);
+    const int ns = p.ns;
+    constexpr int kTcStageBytes = tc_stage_bytes(MODE);
+    // shared-window addresses: stages [ns x 16 (20) KB], then the barriers (8 bytes each)
+    const uint32_t stages = smem_u32(smem_raw);
+    const uint32_t bars = stages + (uint32_t)ns * kTcStageBytes;
+    const uint32_t smem_full = bars;                                   // [kTcMaxStages]
+    const uint32_t smem_empty = bars + 8 * kTcMaxStages;               // [kTcMaxStages]
+    const uint32_t tmem_full = bars + 16 * kTcMaxStages;               // [kTcAccum]
+    const uint32_t tmem_empty = tmem_full + 8 * kTcAccum;              // [kTcAccum]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(smem_raw + (size_t)ns * kTcStageBytes + 16 * kTcMaxStages + 16 * kTcAccum);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int jg = blockIdx.y, tq = blockIdx.z;
@@ -180,8 +205,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
     const int n_i = max(i_end - i_begin, 0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&smem_full[s], 1); mbar_init(&smem_empty[s], 1); }
-        for (int t = 0; t < kTcAccum; ++t) { mbar_init(&tmem_full[t], 1); mbar_init(&tmem_empty[t], 8); }
+        // kModeA: the 8 epilogue warps read their coefficients out of the stage, so they release it too
+        for (int s = 0; s < ns; ++s) { mbar_init(smem_full + 8 * s, 1); mbar_init(smem_empty + 8 * s, MODE == kModeA ? 9 : 1); }
+        for (int t = 0; t < kTcAccum; ++t) { mbar_init(tmem_full + 8 * t, 1); mbar_init(tmem_empty + 8 * t, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -194,41 +220,85 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 8) {
-        // ===== producer =====
-        if (lane == 0) {
-            for (int n = 0; n < n_i; ++n) {
-                const int s = n % kTcStages;
-                mbar_wait(&smem_empty[s], ((n / kTcStages) & 1) ^ 1);
-                mbar_expect_tx(&smem_full[s], kTcStageBytes);
-                const int i = i_begin + n;
-                uint8_t* dst = stages + s * kTcStageBytes;
-                bulk_g2s(dst, p.ua + ((size_t)tq * p.N + i) * 2048, kTcABytes, &smem_full[s]);
-                bulk_g2s(dst + kTcABytes, p.wb + ((size_t)i * p.JG + jg) * 2048, kTcBBytes, &smem_full[s]);
+        // ===== producer: converged warp, one elected lane arms the barrier and issues both copies =====
+        const float* asrc = p.ua + ((size_t)tq * p.N + i_begin) * 2048;
+        const float* bsrc = p.wb + ((size_t)i_begin * p.JG + jg) * 2048;
+        const size_t bstep = (size_t)p.JG * 2048;
+        int s = 0;
+        uint32_t ph = 1;                                 // parity to wait for on smem_empty (first lap passes)
+        // kModeA: + one copy per valid lane tile of the quad: coef[tile][i][8 jg .. +nj][32] (nj * 128 bytes)
+        const int nj = min(kTcJW, p.C - jg * kTcJW);
+        const uint32_t cbytes = (uint32_t)nj * 128u;
+        const size_t ctile = (size_t)p.N * p.C * kLanes;                 // coef elements per lane tile
+        const float* csrc = MODE == kModeA ? p.coef + ((size_t)(tq * 4) * p.N + i_begin) * p.C * kLanes + (size_t)jg * kTcJW * kLanes : nullptr;
+        const size_t cstep = (size_t)p.C * kLanes;
+        const int nvt = min(4, p.nbt - tq * 4);                          // valid lane tiles in this quad (>= 1)
+        const uint32_t txbytes = (uint32_t)kTcOperandBytes + (MODE == kModeA ? (uint32_t)nvt * cbytes : 0u);
+        for (int n = 0; n < n_i; ++n) {
+            mbar_wait(smem_empty + 8 * s, ph);
+            const uint32_t dst = stages + (uint32_t)s * kTcStageBytes, bar = smem_full + 8 * s;
+            if (MODE == kModeA) {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pe, p1, p2, p3;\n\t"
+                    ".reg .b32 cd;\n\t"
+                    "mov.u32 cd, %8;\n\t"
+                    "elect.sync _|pe, 0xffffffff;\n\t"
+                    "setp.gt.and.s32 p1, %14, 1, pe;\n\t"
+                    "setp.gt.and.s32 p2, %14, 2, pe;\n\t"
+                    "setp.gt.and.s32 p3, %14, 3, pe;\n\t"
+                    "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+                    "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%0];\n\t"
+                    "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%6], %7, [%0];\n\t"
+                    "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%10], %9, [%0];\n\t"
+                    "add.u32 cd, cd, 1024;\n\t"
+                    "@p1 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%11], %9, [%0];\n\t"
+                    "add.u32 cd, cd, 1024;\n\t"
+                    "@p2 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%12], %9, [%0];\n\t"
+                    "add.u32 cd, cd, 1024;\n\t"
+                    "@p3 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%13], %9, [%0];\n\t"
+                    "}"
+                    ::"r"(bar), "r"(txbytes), "r"(dst), "l"(asrc), "r"((uint32_t)kTcABytes),
+                      "r"(dst + kTcABytes), "l"(bsrc), "r"((uint32_t)kTcBBytes),
+                      "r"(dst + kTcOperandBytes), "r"(cbytes), "l"(csrc), "l"(csrc + ctile), "l"(csrc + 2 * ctile), "l"(csrc + 3 * ctile),
+                      "r"(nvt)
+                    : "memory");
+                csrc += cstep;
+            } else {
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pe;\n\t"
+                    "elect.sync _|pe, 0xffffffff;\n\t"
+                    "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+                    "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%0];\n\t"
+                    "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%6], %7, [%0];\n\t"
+                    "}"
+                    ::"r"(bar), "r"(txbytes), "r"(dst), "l"(asrc), "r"((uint32_t)kTcABytes),
+                      "r"(dst + kTcABytes), "l"(bsrc), "r"((uint32_t)kTcBBytes)
+                    : "memory");
             }
+            asrc += 2048;
+            bsrc += bstep;
+            if (++s == ns) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
     } else if (warp == 9) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            // kind::tf32, D = f32, A/B K-major, N = 128, M = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int n = 0; n < n_i; ++n) {
-                const int s = n % kTcStages, t = n % kTcAccum;
-                mbar_wait(&tmem_empty[t], ((n / kTcAccum) & 1) ^ 1);
-                mbar_wait(&smem_full[s], (n / kTcStages) & 1);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(stages + s * kTcStageBytes), b0 = a0 + kTcABytes;
-                const uint64_t a_hi = umma_desc(a0, 2048, 128), a_lo = umma_desc(a0 + 4096, 2048, 128);
-                const uint64_t b_hi = umma_desc(b0, 2048, 128), b_lo = umma_desc(b0 + 4096, 2048, 128);
-                const uint32_t d = tmem_base + (uint32_t)(t * kTcN);
-                umma_tf32(d, a_lo, b_hi, idesc, 0);
-                umma_tf32(d, a_hi, b_lo, idesc, 1);
-                umma_tf32(d, a_hi, b_hi, idesc, 1);
-                umma_commit(&smem_empty[s]);          // operands of stage s consumed
-                umma_commit(&tmem_full[t]);           // accumulator t complete
-            }
+        // ===== MMA issuer: the whole warp runs the loop converged, one elected lane issues =====
+        // kind::tf32, D = f32, A/B K-major, N = 128, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // descriptors differ between stages only in the 14-bit start-address field (bytes >> 4)
+        const uint64_t desc0 = umma_desc(stages, 2048, 128);
+        int s = 0;
+        uint32_t sph = 0;
+        for (int n = 0; n < n_i; ++n) {
+            const int t = n & (kTcAccum - 1);
+            mbar_wait(tmem_empty + 8 * t, ((n >> 2) & 1) ^ 1);
+            mbar_wait(smem_full + 8 * s, sph);
+            tc_fence_after();
+            const uint64_t a_hi = desc0 + (uint64_t)((s * kTcStageBytes) >> 4);
+            const uint64_t a_lo = a_hi + (4096 >> 4), b_hi = a_hi + (kTcABytes >> 4), b_lo = b_hi + (4096 >> 4);
+            umma_stage(tmem_base + (uint32_t)(t * kTcN), a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full + 8 * t);
+            if (++s == ns) { s = 0; sph ^= 1; }
         }
-        __syncwarp();
     } else {
         // ===== epilogue: warp w -> samples of lane tile 4*tq + w%4, capsules j0 .. j0+3 =====
         const int q = warp & 3, jh = warp >> 2;
@@ -251,30 +321,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                     }
                 }
         }
-        float cn[4] = {0.f, 0.f, 0.f, 0.f};
-        auto load_coef = [&](int i) {
-            if (MODE == kModeA && tvalid) {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                    cn[jj] = (j0 + jj < p.C) ? __ldg(p.coef + (((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane) : 0.f;
-            }
-        };
-        if (n_i > 0) load_coef(i_begin);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * 64);
+        // kModeA: this warp's coefficients inside a stage: [q][jh*4 + jj][lane]
+        const uint32_t coef_off = (uint32_t)kTcOperandBytes + (uint32_t)((q * kTcJW + jh * 4) * kLanes + lane) * 4u;
+        int s = 0;
+        uint32_t sph = 0;
         for (int n = 0; n < n_i; ++n) {
-            const int t = n % kTcAccum;
+            const int t = n & (kTcAccum - 1);
             const int i = i_begin + n;
-            float cc[4];
+            float cc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (MODE == kModeA) {
+                mbar_wait(smem_full + 8 * s, sph);               // the bulk copies of stage s have landed
+                if (tvalid) {
+                    const uint32_t ca = stages + (uint32_t)s * kTcStageBytes + coef_off;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) cc[jj] = cn[jj];
-            if (n + 1 < n_i) load_coef(i + 1);
-            mbar_wait(&tmem_full[t], (n / kTcAccum) & 1);
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (j0 + jj < p.C) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cc[jj]) : "r"(ca + jj * 128) : "memory");
+                }
+            }
+            mbar_wait(tmem_full + 8 * t, (n >> 2) & 1);
             tc_fence_after();
             float uh[64];
             tmem_ld64(lane_base + (uint32_t)(t * kTcN), uh);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[t]);      // accumulator t may be overwritten
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * t);  // accumulator t may be overwritten
             if (MODE == kModeL) {
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
@@ -290,6 +361,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 #pragma unroll
                     for (int d = 0; d < 16; ++d) acc[jj][d] = fmaf(f, uh[jj * 16 + d], acc[jj][d]);
                 }
+            }
+            if (MODE == kModeA) {
+                // the FMAs above consumed cc, so the shared loads are complete: release our share of stage s
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_empty + 8 * s);
+                if (++s == ns) { s = 0; sph ^= 1; }
             }
         }
         if (MODE != kModeL && tvalid) {
@@ -314,6 +391,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 
 }  // namespace
 
+int g_tc_stages = 10;
+
 size_t tc_ua_floats(int B, int N) { return (size_t)cdiv(B > 0 ? B : 1, 128) * N * 2048; }
 size_t tc_wb_floats(int N, int C) { return (size_t)N * cdiv(C, kTcJW) * 2048; }
 
@@ -337,7 +416,9 @@ int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* 
     PassTcParams tp{};
     tp.ua = ua; tp.wb = wb; tp.coef = pp.coef; tp.X = pp.X; tp.out = pp.out;
     tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, kTcJW); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
-    const size_t smem = (size_t)kTcStages * kTcStageBytes + 256;
+    tp.ns = g_tc_stages < 2 ? 2 : g_tc_stages > kTcMaxStages ? kTcMaxStages : g_tc_stages;
+    while ((size_t)tp.ns * tc_stage_bytes(mode) + 512 > 227 * 1024) --tp.ns;      // 227 KB of dynamic smem per CTA
+    const size_t smem = (size_t)tp.ns * tc_stage_bytes(mode) + 512;
     dim3 grid(pl.IS, tp.JG, cdiv(pl.nbt, 4)), block(kTcThreads);
 #define CAPS_LAUNCH_TC(MODE)                                                                             \
     {                                                                                                    \

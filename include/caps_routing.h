@@ -119,6 +119,7 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
  *   name = "isplit" forced number of splits of the N range (0 = auto)
  *   name = "tc"   1 (default): tcgen05 tensor-core pass kernel where it applies (D == 16, C >= 4);
  *                 0: fp32-FMA pass kernel everywhere
+ *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
  *                 (D == 16, C >= 7); 0: fp32-FMA gradient kernel everywhere
  *   name = "profile" 1: bracket every launch with CUDA events (see caps_profile_collect)
