@@ -30,7 +30,8 @@ namespace {
 constexpr int kGmIT = 8;          // input capsules per CTA
 constexpr int kGmJW = 8;          // warps = output capsules per CTA
 constexpr int kGmDub = 4;         // capsules per du reduction round
-constexpr int kGmGStride = 24;    // floats per sample row of the G tile (bank-conflict-free fragment reads)
+constexpr int kGmGStride = 20;    // floats per sample row of the G tile: 16-byte stores and the du fragment reads are
+                                  // bank-conflict free, the dW fragment reads are 2-way on half their lanes
 
 __device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                  uint32_t b0, uint32_t b1) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
     float* dWsm = Wfrag + IT * JW * 256;                   // [IT][JW][32 lanes][4]
     float* Gs = dWsm + IT * JW * 128;                      // [JW][32][GS]
     float* Us = Gs + JW * 32 * GS;                         // [JW][32][8]
-    float* dusm = Us + JW * 32 * 8;                        // [JW][DUB][32 lanes][8]
+    float* dusm = Us + JW * 32 * 8;                        // [JW][DUB][half 2][32 lanes][4]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
@@ -199,20 +200,20 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
                         duf[mt * 4 + 0] = cc[0]; duf[mt * 4 + 1] = cc[1]; duf[mt * 4 + 2] = cc[2]; duf[mt * 4 + 3] = cc[3];
                     }
                 }
-                float* ds = dusm + (size_t)((warp * DUB + ii) * 32 + lane) * 8;
+                float* ds = dusm + (size_t)((warp * DUB + ii) * 2) * 128 + lane * 4;   // [warp][ii][half][lane][4]
                 st4(ds, make_float4(duf[0], duf[1], duf[2], duf[3]));
-                st4(ds + 4, make_float4(duf[4], duf[5], duf[6], duf[7]));
+                st4(ds + 128, make_float4(duf[4], duf[5], duf[6], duf[7]));
             }
             __syncthreads();
             // sum the 8 capsules' du fragments; thread <-> (ii, lane, half)
             for (int e = threadIdx.x; e < DUB * 64; e += NT) {
-                const int half = e & 1, l = (e >> 1) & 31, ii = e >> 6;
+                const int l = e & 31, half = (e >> 5) & 1, ii = e >> 6;
                 const int il = ib + ii;
                 if (il < ni) {
                     float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int w = 0; w < JW; ++w) {
-                        const float4 x = *reinterpret_cast<const float4*>(dusm + (size_t)((w * DUB + ii) * 32 + l) * 8 + half * 4);
+                        const float4 x = *reinterpret_cast<const float4*>(dusm + (size_t)(((w * DUB + ii) * 2 + half) * 32 + l) * 4);
                         sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
                     }
                     // fragment (mt = half): c0 (b = 16mt+gg, k = 2tt), c1 (.., k = 2tt+1), c2 (b + 8, k = 2tt), c3 (b + 8, 2tt+1)

@@ -776,10 +776,11 @@ static __global__ void k_fma_peak(float* __restrict__ sink, int iters, float m0,
         m[t] = m0 - 1e-6f * (float)(threadIdx.x + t);
         c[t] = c0 + 1e-7f * (float)(threadIdx.x * 3 + t);
     }
-#pragma unroll 4
-    for (int it = 0; it < iters; ++it) {
+    for (int it = 0; it < iters; it += 4) {
 #pragma unroll
-        for (int t = 0; t < 16; ++t) a[t] = fmaf(a[t], m[t & 3], c[(t >> 2) & 3]);
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int t = 0; t < 16; ++t) a[t] = fmaf(a[t], m[t & 3], c[(t >> 2) & 3]);
     }
     float s = 0.f;
 #pragma unroll
