@@ -30,6 +30,7 @@ namespace {
 constexpr int kGmIT = 8;          // input capsules per CTA
 constexpr int kGmJW = 8;          // warps = output capsules per CTA
 constexpr int kGmDub = 4;         // capsules per du reduction round
+constexpr int kGmStages = 8;      // operand ring depth (units in flight per CTA)
 constexpr int kGmGStride = 20;    // floats per sample row of the G tile: 16-byte stores and the du fragment reads are
                                   // bank-conflict free, the dW fragment reads are 2-way on half their lanes
 
@@ -60,16 +61,47 @@ __device__ __forceinline__ void mma3(float (&c)[4], const float (&a)[4], const f
     mma_tf32_m16n8k8(c, a0, a1, a2, a3, b0, b1);
 }
 
-// grid = (ceil(N/8), ceil(C/8)); block = 256.  K = 8, D = 16 only.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > 8000000000LL) __trap();      // ~4 s: a protocol bug, not a long wait
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+// grid = (ceil(N/8), ceil(C/8)); block = 288 (8 consumer warps + 1 producer warp).  K = 8, D = 16 only.
+//
+// The per-(b,i) operands -- the u tile and the 2R-2 coefficient rows of the CTA's 8 capsules -- are
+// streamed into a shared-memory ring by cp.async.bulk, kGmStages units ahead.  With plain (even
+// register-prefetched) loads the kernel ran at exactly one loaded-HBM latency (~1750 cycles) per unit
+// whatever the math did (11 ms with ALL the math removed): 8 warps with one unit of loads in flight each
+// is far too little memory-level parallelism.
 template <int M>
-__global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
-    constexpr int IT = kGmIT, JW = kGmJW, DUB = kGmDub, GS = kGmGStride, NT = 32 * JW;
+__global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
+    constexpr int IT = kGmIT, JW = kGmJW, DUB = kGmDub, GS = kGmGStride, NT = 32 * JW;     // NT: consumer threads
+    constexpr int NS = kGmStages, SF = 256 + (M - 1) * JW * 32;       // stage: u tile + up to M-1 coefficient rows
     extern __shared__ __align__(16) float smem[];
     float* Wfrag = smem;                                   // [IT][JW][ks 2][hl 2][32 lanes][2]
     float* dWsm = Wfrag + IT * JW * 256;                   // [IT][JW][32 lanes][4]
     float* Gs = dWsm + IT * JW * 128;                      // [JW][32][GS]
-    float* Us = Gs + JW * 32 * GS;                         // [JW][32][8]
-    float* dusm = Us + JW * 32 * 8;                        // [JW][DUB][half 2][32 lanes][4]
+    float* dusm = Gs + JW * 32 * GS;                       // [JW][DUB][half 2][32 lanes][4]
+    float* ring = dusm + JW * DUB * 256;                   // [NS][ u tile [2][32][4] | coef rows [M-1][JW][32] ]
+    const uint32_t bars = smem_u32(ring + NS * SF);        // full[NS], empty[NS]
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * NS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
@@ -81,7 +113,7 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
     const int njv = min(JW, p.C - j0);
 
     // W^T fragments for du:  B[d][k] = W[k][d];  b0 = (d = t + 8 ks, k = g), b1 = (d = t + 4 + 8 ks, k = g)
-    for (int e = threadIdx.x; e < IT * JW * 64; e += NT) {
+    for (int e = threadIdx.x; e < IT * JW * 64; e += blockDim.x) {
         const int l = e & 31, ks = (e >> 5) & 1, w = (e >> 6) % JW, il = e / (64 * JW);
         const int gg = l >> 2, tt = l & 3;
         float w0 = 0.f, w1 = 0.f;
@@ -97,35 +129,57 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
         *reinterpret_cast<float2*>(dst + l * 2) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
         *reinterpret_cast<float2*>(dst + 64 + l * 2) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
     }
-    for (int e = threadIdx.x; e < IT * JW * 128; e += NT) dWsm[e] = 0.f;
+    for (int e = threadIdx.x; e < IT * JW * 128; e += blockDim.x) dWsm[e] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < NS; ++q) { mbar_init(bar_full + 8 * q, 1); mbar_init(bar_empty + 8 * q, JW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
+    if (warp == JW) {
+        // ===== producer warp: one elected lane streams (tile, il) stages, NS ahead =====
+        const uint32_t ubytes = 2 * 32 * 4 * 4, cbytes = (uint32_t)njv * 128u;
+        int ncoef = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) ncoef += p.coef[m] != nullptr;
+        const uint32_t txbytes = ubytes + (uint32_t)ncoef * cbytes;
+        int q = 0;
+        uint32_t ph = 1;
+        for (int tile = 0; tile < p.nbt; ++tile)
+            for (int il = 0; il < ni; ++il) {
+                mbar_wait(bar_empty + 8 * q, ph);
+                if (lane == 0) {
+                    const size_t ti = (size_t)tile * p.N + i0 + il;
+                    const uint32_t dst = smem_u32(ring + q * SF), bar = bar_full + 8 * q;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(txbytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(p.ut + ti * 256), "r"(ubytes), "r"(bar) : "memory");
+                    uint32_t cd = dst + ubytes;
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+                        if (p.coef[m] != nullptr) {
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(cd), "l"(p.coef[m] + (ti * p.C + j0) * kLanes), "r"(cbytes), "r"(bar) : "memory");
+                            cd += JW * 128;
+                        }
+                }
+                __syncwarp();
+                if (++q == NS) { q = 0; ph ^= 1; }
+            }
+        return;                                             // the consumers synchronise among themselves (named barrier 1)
+    }
+
     float* Gw = Gs + warp * 32 * GS;
-    float* Uw = Us + warp * 32 * 8;
-
-    // per-(b,i) operands of the NEXT unit are fetched while the current one computes (8 warps per
-    // SM cannot hide a ~1000-cycle global load by themselves)
-    float4 un0 = make_float4(0.f, 0.f, 0.f, 0.f), un1 = un0;
-    float aln[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) aln[m] = 0.f;
-    const float* coefp[M];
+    // slot of this warp's coefficient m inside a stage (only non-constant terms are staged, in order)
+    int cslot[M];
     float cconst[M];
+    {
+        int n = 0;
 #pragma unroll
-    for (int m = 0; m < M; ++m) { coefp[m] = p.coef[m]; cconst[m] = p.cconst[m]; }
-    const float* utp = p.ut;
-    const size_t cstride = (size_t)p.C * kLanes;           // coef elements between consecutive i
-    auto load_unit = [&](int tile, int il) {
-        const size_t ti = (size_t)tile * p.N + i0 + il;
-        const float* up = utp + ti * (2 * kLanes * 4) + lane * 4;
-        un0 = ldg4(up);
-        un1 = ldg4(up + kLanes * 4);
-        const size_t co = ti * cstride + (size_t)j * kLanes + lane;
-#pragma unroll
-        for (int m = 0; m < M; ++m) aln[m] = coefp[m] != nullptr ? __ldg(coefp[m] + co) : cconst[m];
-    };
-    if (jvalid && p.nbt > 0) load_unit(0, 0);
-
+        for (int m = 0; m < M; ++m) { cslot[m] = p.coef[m] != nullptr ? n++ : -1; cconst[m] = p.cconst[m]; }
+    }
+    int sq = 0;                                             // ring position of the current unit
+    uint32_t sph = 0;
     for (int tile = 0; tile < p.nbt; ++tile) {
         float xr[M][16];
         if (jvalid) {
@@ -144,25 +198,22 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
                 float duf[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) duf[e] = 0.f;
+                const float* stg = ring + sq * SF;          // this unit's stage: [u: kq][32][4] then coefficient rows
+                if (il < ni) mbar_wait(bar_full + 8 * sq, sph);
                 if (jvalid && il < ni) {
-                    const float4 u0 = un0, u1 = un1;
                     float G[16];
 #pragma unroll
                     for (int d = 0; d < 16; ++d) G[d] = 0.f;
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        const float al = aln[m];
+                        const float al = cslot[m] >= 0 ? stg[256 + (cslot[m] * JW + warp) * 32 + lane] : cconst[m];
 #pragma unroll
                         for (int d = 0; d < 16; ++d) G[d] = fmaf(al, xr[m][d], G[d]);
                     }
-                    if (il + 1 < ni) load_unit(tile, il + 1);
-                    else if (tile + 1 < p.nbt) load_unit(tile + 1, 0);
-                    __syncwarp();                                   // previous round's fragment reads are done
+                    __syncwarp();                                   // previous unit's fragment reads are done
 #pragma unroll
                     for (int dq = 0; dq < 4; ++dq)
                         st4(Gw + lane * GS + dq * 4, make_float4(G[dq * 4], G[dq * 4 + 1], G[dq * 4 + 2], G[dq * 4 + 3]));
-                    st4(Uw + lane * 8, u0);
-                    st4(Uw + lane * 8 + 4, u1);
                     __syncwarp();
                     // ---- dW[d][k] += sum_b G[b][d] u[b][k] : 4 chunks of 8 samples, two accumulators
                     float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -171,7 +222,9 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
                         const float* gr0 = Gw + (8 * c + t) * GS;
                         const float* gr1 = Gw + (8 * c + t + 4) * GS;
                         const float a[4] = {gr0[g], gr0[g + 8], gr1[g], gr1[g + 8]};
-                        const float b[2] = {Uw[(8 * c + t) * 8 + g], Uw[(8 * c + t + 4) * 8 + g]};
+                        // u[b][k] straight out of the stage: (k >> 2) * 128 + b * 4 + (k & 3)
+                        const float* ub = stg + (g >> 2) * 128 + (8 * c + t) * 4 + (g & 3);
+                        const float b[2] = {ub[0], ub[16]};
                         if (c & 1) mma3(c1, a, b); else mma3(c0, a, b);
                     }
                     float* dw = dWsm + (size_t)((il * JW + warp) * 32 + lane) * 4;     // lane-private: no hazard
@@ -200,11 +253,16 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
                         duf[mt * 4 + 0] = cc[0]; duf[mt * 4 + 1] = cc[1]; duf[mt * 4 + 2] = cc[2]; duf[mt * 4 + 3] = cc[3];
                     }
                 }
+                if (il < ni) {                              // every consumer warp releases every stage
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty + 8 * sq);
+                    if (++sq == NS) { sq = 0; sph ^= 1; }
+                }
                 float* ds = dusm + (size_t)((warp * DUB + ii) * 2) * 128 + lane * 4;   // [warp][ii][half][lane][4]
                 st4(ds, make_float4(duf[0], duf[1], duf[2], duf[3]));
                 st4(ds + 128, make_float4(duf[4], duf[5], duf[6], duf[7]));
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             // sum the 8 capsules' du fragments; thread <-> (ii, lane, half)
             for (int e = threadIdx.x; e < DUB * 64; e += NT) {
                 const int l = e & 31, half = (e >> 5) & 1, ii = e >> 6;
@@ -224,7 +282,7 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
                     *reinterpret_cast<float2*>(dst + (b0 + 8) * 4 + kk) = make_float2(sum.z, sum.w);
                 }
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
 
@@ -245,11 +303,11 @@ __global__ void __launch_bounds__(32 * kGmJW, 1) k_grad_mma(GradParams p) {
 
 template <int M>
 int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
-    const size_t smem = ((size_t)kGmIT * kGmJW * 256 + kGmIT * kGmJW * 128 + kGmJW * 32 * kGmGStride + kGmJW * 32 * 8 +
-                         kGmJW * kGmDub * 32 * 8) * sizeof(float);
+    const size_t smem = ((size_t)kGmIT * kGmJW * 256 + kGmIT * kGmJW * 128 + kGmJW * 32 * kGmGStride + kGmJW * kGmDub * 256 +
+                         (size_t)kGmStages * (256 + (M - 1) * kGmJW * 32)) * sizeof(float) + 16 * kGmStages;
     auto kern = k_grad_mma<M>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, kGmJW)), block(32 * kGmJW);
+    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, kGmJW)), block(32 * kGmJW + 32);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();
     return 0;

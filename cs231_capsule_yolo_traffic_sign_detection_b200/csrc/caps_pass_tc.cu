@@ -423,7 +423,8 @@ int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* 
 #define CAPS_LAUNCH_TC(MODE)                                                                             \
     {                                                                                                    \
         auto kern = k_pass_tc<MODE>;                                                                     \
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        { static size_t attr_set = 0;   /* per instantiation; the attribute is per device function, set once (or when it grows) */ \
+          if (smem > attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; } }    \
         kern<<<grid, block, smem, st>>>(tp);                                                             \
     }
     if (mode == kModeAUniform) CAPS_LAUNCH_TC(kModeAUniform)
