@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libcaps_routing.so')
+LIB_PATH = os.environ.get('CAPS_ROUTING_LIB') or os.path.join(HERE, 'libcaps_routing.so')   # env override: A/B experiments
 
 ABI_VERSION = 1
 MARGIN_SCRATCH_FLOATS = 2048

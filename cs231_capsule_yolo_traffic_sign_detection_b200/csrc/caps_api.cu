@@ -204,6 +204,7 @@ int caps_set_tuning(const char* name, int value) {
         g_tune_spt = value;
         return 0;
     }
+    if (!strcmp(name, "tcdbg")) { g_tc_dbg = value; return 0; }
     if (!strcmp(name, "tcstages")) { if (value < 2 || value > 12) return fail(CAPS_E_BADARG, "tcstages must be in [2,12]"); g_tc_stages = value; return 0; }
     if (!strcmp(name, "gradmma")) { g_tune_gradmma = value != 0; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }

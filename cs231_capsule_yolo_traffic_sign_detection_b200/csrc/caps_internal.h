@@ -37,6 +37,7 @@ int launch_pass(const Plan& pl, int mode, const PassParams& pp, cudaStream_t st)
 int launch_grad(const Plan& pl, const GradParams& gp, cudaStream_t st);             // caps_grad.cu
 int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st);         // caps_grad_mma.cu (D == 16, JW == 8)
 // caps_pass_tc.cu: tcgen05 pass kernel (D == 16 only) and its operand preparation
+extern int g_tc_dbg;                    // timing experiments only
 extern int g_tc_stages;                 // smem ring depth of the tcgen05 pass kernel (tuning knob "tcstages")
 size_t tc_ua_floats(int B, int N);
 size_t tc_wb_floats(int N, int C);

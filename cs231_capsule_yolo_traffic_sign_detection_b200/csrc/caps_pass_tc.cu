@@ -10,7 +10,7 @@
 // halves and pre-arranged in the canonical no-swizzle K-major core-matrix layout by the prep
 // kernels below, so that one pipeline stage is two cp.async.bulk copies (8 KB of A, 8 KB of B).
 //
-// Warp roles (320 threads):  warps 0-7 epilogue, warp 8 bulk-copy producer, warp 9 MMA issuer.
+// Warp roles (384 threads):  warps 0-7 epilogue, warps 8-9 bulk-copy producers, warps 10-11 MMA issuers.
 //   producer : waits smem_empty[s], arms smem_full[s] with expect_tx, issues the two bulk copies
 //   MMA      : waits smem_full[s] and tmem_empty[t], issues 3 tcgen05.mma, commits to
 //              smem_empty[s] (operands consumed) and tmem_full[t] (accumulator ready)
@@ -26,7 +26,11 @@ namespace caps {
 namespace {
 
 constexpr int kTcMaxStages = 12;      // smem ring depth is a launch parameter (<= 12 x 16 KB)
-constexpr int kTcAccum = 4;           // TMEM ring (4 x 128 columns); power of two (index = n & 3, phase = (n >> 2) & 1)
+#ifndef CAPS_TC_ACCUM_LOG2
+#define CAPS_TC_ACCUM_LOG2 2
+#endif
+constexpr int kTcAccumLog2 = CAPS_TC_ACCUM_LOG2;
+constexpr int kTcAccum = 1 << kTcAccumLog2;           // TMEM ring (4 x 128 columns); power of two (index = n & 3, phase = (n >> kTcAccumLog2) & 1)
 constexpr int kTcJW = 8;              // capsules per CTA  -> N = 128
 constexpr int kTcN = 128;
 constexpr int kTcABytes = 2 * 2 * 128 * 16;      // [hi/lo][kq][128 rows][16 B] = 8 KB
@@ -34,7 +38,12 @@ constexpr int kTcBBytes = 2 * 2 * kTcN * 16;     // 8 KB
 constexpr int kTcOperandBytes = kTcABytes + kTcBBytes;       // 16 KB of MMA operands per stage
 constexpr int kTcCoefBytes = 4 * kTcJW * 32 * 4;              // kModeA: [4 lane tiles][8 capsules][32 lanes] coefficients
 __host__ __device__ constexpr int tc_stage_bytes(int mode) { return kTcOperandBytes + (mode == kModeA ? kTcCoefBytes : 0); }
-constexpr int kTcThreads = 320;
+constexpr int kTcEpiWarps = 8;        // epilogue warps: 2 per TMEM lane quarter, 4 capsules (64 columns) each
+constexpr int kTcIssuers = 2;         // producer warps and MMA-issuer warps: each takes every kTcIssuers-th stage, because one
+                                      // thread's wait -> issue chain (~250 cycles: mbarrier.try_wait alone is ~100) is longer
+                                      // than the 235 cycles of tensor work it feeds
+constexpr int kTcJPW = kTcJW / (kTcEpiWarps / 4);   // capsules per epilogue warp
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 2 * kTcIssuers);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -77,25 +86,53 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 //   D  = a_lo*b_hi ;  D += a_hi*b_lo ;  D += a_hi*b_hi        (3xTF32)
 // then two commits: bar_smem (operands consumed) and bar_tmem (accumulator complete).
 __device__ __forceinline__ void umma_stage(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                           uint32_t idesc, uint32_t bar_smem, uint32_t bar_tmem) {
+                                           uint32_t idesc, uint32_t bar_smem, uint32_t bar_tmem,
+                                           uint32_t accum_first = 0, uint32_t commit_tmem = 1) {
     asm volatile(
         "{\n\t"
-        ".reg .pred pe, pf, pt;\n\t"
+        ".reg .pred pe, pf, pt, pc;\n\t"
         "elect.sync _|pe, 0xffffffff;\n\t"
-        "setp.ne.b32 pf, 0, 0;\n\t"
+        "setp.ne.b32 pf, %8, 0;\n\t"
         "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.and.b32 pc, %9, 0, pe;\n\t"
         "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, pf;\n\t"
         "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, pt;\n\t"
         "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, pt;\n\t"
         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+        "@pc tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
         "}"
-        ::"r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_smem), "r"(bar_tmem)
+        ::"r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar_smem), "r"(bar_tmem),
+          "r"(accum_first), "r"(commit_tmem)
         : "memory");
+}
+// two fp32 FMAs in one instruction (Blackwell FFMA2): d = a * b + d on a register pair.  The epilogue is
+// issue-bound (two warps per scheduler), so halving its FMA instruction count is what matters.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    uint64_t a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// 32 consecutive fp32 columns of this warp's 32 TMEM lanes -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 // 64 consecutive fp32 columns of this warp's 32 TMEM lanes -> 64 registers per thread
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     uint32_t r[64];
@@ -115,6 +152,10 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+template <int NC> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]);
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld<64>(uint32_t taddr, float (&v)[64]) { tmem_ld64(taddr, v); }
 
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
@@ -182,6 +223,7 @@ struct PassTcParams {
     const float* X;      // kModeL: [nbt][C][4][32][4]
     float* out;          // kModeL: [nbt][N][C][32];  kModeA*: part [IS][nbt][C][4][32][4]
     int N, C, JG, nbt, i_per_split, ns;
+    int dbg;             // TIMING EXPERIMENTS ONLY (tuning knob "tcdbg"): 1 = skip the L-mode stores, 2 = skip the coefficient copies
 };
 
 template <int MODE>
@@ -206,11 +248,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 
     if (threadIdx.x == 0) {
         // kModeA: the 8 epilogue warps read their coefficients out of the stage, so they release it too
-        for (int s = 0; s < ns; ++s) { mbar_init(smem_full + 8 * s, 1); mbar_init(smem_empty + 8 * s, MODE == kModeA ? 9 : 1); }
-        for (int t = 0; t < kTcAccum; ++t) { mbar_init(tmem_full + 8 * t, 1); mbar_init(tmem_empty + 8 * t, 8); }
+        for (int s = 0; s < ns; ++s) { mbar_init(smem_full + 8 * s, 1); mbar_init(smem_empty + 8 * s, MODE == kModeA ? kTcEpiWarps + 1 : 1); }
+        for (int t = 0; t < kTcAccum; ++t) { mbar_init(tmem_full + 8 * t, 1); mbar_init(tmem_empty + 8 * t, kTcEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == kTcEpiWarps + kTcIssuers) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -219,22 +261,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (warp == 8) {
+    if (warp >= kTcEpiWarps && warp < kTcEpiWarps + kTcIssuers) {
         // ===== producer: converged warp, one elected lane arms the barrier and issues both copies =====
-        const float* asrc = p.ua + ((size_t)tq * p.N + i_begin) * 2048;
-        const float* bsrc = p.wb + ((size_t)i_begin * p.JG + jg) * 2048;
-        const size_t bstep = (size_t)p.JG * 2048;
-        int s = 0;
+        // producer w takes stages n = w, w + NI, w + 2 NI, ...  (uniform mode: a single producer)
+        constexpr int NI = (MODE == kModeAUniform) ? 1 : kTcIssuers;
+        const int w = warp - kTcEpiWarps;
+        if (w >= NI) goto role_done;
+        const float* asrc = p.ua + ((size_t)tq * p.N + i_begin + w) * 2048;
+        const float* bsrc = p.wb + ((size_t)(i_begin + w) * p.JG + jg) * 2048;
+        const size_t bstep = (size_t)p.JG * 2048 * NI;
+        int s = w;
         uint32_t ph = 1;                                 // parity to wait for on smem_empty (first lap passes)
         // kModeA: + one copy per valid lane tile of the quad: coef[tile][i][8 jg .. +nj][32] (nj * 128 bytes)
         const int nj = min(kTcJW, p.C - jg * kTcJW);
         const uint32_t cbytes = (uint32_t)nj * 128u;
         const size_t ctile = (size_t)p.N * p.C * kLanes;                 // coef elements per lane tile
-        const float* csrc = MODE == kModeA ? p.coef + ((size_t)(tq * 4) * p.N + i_begin) * p.C * kLanes + (size_t)jg * kTcJW * kLanes : nullptr;
-        const size_t cstep = (size_t)p.C * kLanes;
-        const int nvt = min(4, p.nbt - tq * 4);                          // valid lane tiles in this quad (>= 1)
+        const float* csrc = MODE == kModeA ? p.coef + ((size_t)(tq * 4) * p.N + i_begin + w) * p.C * kLanes + (size_t)jg * kTcJW * kLanes : nullptr;
+        const size_t cstep = (size_t)p.C * kLanes * NI;
+        const int nvt = (p.dbg & 2) ? 0 : min(4, p.nbt - tq * 4);        // valid lane tiles in this quad (>= 1)
         const uint32_t txbytes = (uint32_t)kTcOperandBytes + (MODE == kModeA ? (uint32_t)nvt * cbytes : 0u);
-        for (int n = 0; n < n_i; ++n) {
+        for (int n = w; n < n_i; n += NI) {
             mbar_wait(smem_empty + 8 * s, ph);
             const uint32_t dst = stages + (uint32_t)s * kTcStageBytes, bar = smem_full + 8 * s;
             if (MODE == kModeA) {
@@ -250,7 +296,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                     "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
                     "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%0];\n\t"
                     "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%5], [%6], %7, [%0];\n\t"
-                    "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%10], %9, [%0];\n\t"
+                    "setp.gt.and.s32 p1, %14, 0, pe;\n\t"
+                    "@p1 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%10], %9, [%0];\n\t"
+                    "setp.gt.and.s32 p1, %14, 1, pe;\n\t"
                     "add.u32 cd, cd, 1024;\n\t"
                     "@p1 cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [cd], [%11], %9, [%0];\n\t"
                     "add.u32 cd, cd, 1024;\n\t"
@@ -277,42 +325,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                       "r"(dst + kTcABytes), "l"(bsrc), "r"((uint32_t)kTcBBytes)
                     : "memory");
             }
-            asrc += 2048;
+            asrc += 2048 * NI;
             bsrc += bstep;
-            if (++s == ns) { s = 0; ph ^= 1; }
+            s += NI;
+            if (s >= ns) { s -= ns; ph ^= 1; }
         }
-    } else if (warp == 9) {
+    } else if (warp >= kTcEpiWarps + kTcIssuers) {
         // ===== MMA issuer: the whole warp runs the loop converged, one elected lane issues =====
         // kind::tf32, D = f32, A/B K-major, N = 128, M = 128
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         // descriptors differ between stages only in the 14-bit start-address field (bytes >> 4)
         const uint64_t desc0 = umma_desc(stages, 2048, 128);
-        int s = 0;
+        // issuer w takes stages n = w, w + NI, ...: stages are independent (own smem slot, own accumulator), and a
+        // tcgen05.commit only tracks the MMAs of the thread that executes it.  Uniform mode is one dependent
+        // accumulation chain, so it keeps a single issuer.
+        constexpr int NI = (MODE == kModeAUniform) ? 1 : kTcIssuers;
+        const int w = warp - kTcEpiWarps - kTcIssuers;
+        if (w >= NI) goto role_done;
+        int s = w;
         uint32_t sph = 0;
-        for (int n = 0; n < n_i; ++n) {
-            const int t = n & (kTcAccum - 1);
-            mbar_wait(tmem_empty + 8 * t, ((n >> 2) & 1) ^ 1);
+        for (int n = w; n < n_i; n += NI) {
+            const int t = (MODE == kModeAUniform) ? 0 : (n & (kTcAccum - 1));
+            if (MODE != kModeAUniform) mbar_wait(tmem_empty + 8 * t, ((n >> kTcAccumLog2) & 1) ^ 1);
             mbar_wait(smem_full + 8 * s, sph);
             tc_fence_after();
             const uint64_t a_hi = desc0 + (uint64_t)((s * kTcStageBytes) >> 4);
             const uint64_t a_lo = a_hi + (4096 >> 4), b_hi = a_hi + (kTcABytes >> 4), b_lo = b_hi + (4096 >> 4);
-            umma_stage(tmem_base + (uint32_t)(t * kTcN), a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full + 8 * t);
-            if (++s == ns) { s = 0; sph ^= 1; }
+            if (MODE == kModeAUniform)
+                // uniform couplings: sum_i u_hat_i IS one long GEMM over (i,k): accumulate in TMEM across all the
+                // stages, signal the epilogue once
+                umma_stage(tmem_base, a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full, n > 0, n == n_i - 1);
+            else
+                umma_stage(tmem_base + (uint32_t)(t * kTcN), a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full + 8 * t);
+            s += NI;
+            if (s >= ns) { s -= ns; sph ^= 1; }
         }
     } else {
-        // ===== epilogue: warp w -> samples of lane tile 4*tq + w%4, capsules j0 .. j0+3 =====
+        // ===== epilogue: warp w -> samples of lane tile 4*tq + w%4, capsules j0 .. j0+JPW-1 =====
+        constexpr int JPW = kTcJPW, NC = 16 * JPW;
         const int q = warp & 3, jh = warp >> 2;
         const int tile = tq * 4 + q;
         const bool tvalid = tile < p.nbt;
-        const int j0 = jg * kTcJW + jh * 4;
-        float acc[4][16];                 // A modes: running sums; L mode: the probe vectors X[b,j,:]
+        const int j0 = jg * kTcJW + jh * JPW;
+        float acc[JPW][16];                 // A modes: running sums; L mode: the probe vectors X[b,j,:]
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
+        for (int jj = 0; jj < JPW; ++jj)
 #pragma unroll
             for (int d = 0; d < 16; ++d) acc[jj][d] = 0.f;
         if (MODE == kModeL && tvalid) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+            for (int jj = 0; jj < JPW; ++jj)
                 if (j0 + jj < p.C) {
 #pragma unroll
                     for (int dq = 0; dq < 4; ++dq) {
@@ -321,45 +383,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                     }
                 }
         }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * 64);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * NC);
         // kModeA: this warp's coefficients inside a stage: [q][jh*4 + jj][lane]
-        const uint32_t coef_off = (uint32_t)kTcOperandBytes + (uint32_t)((q * kTcJW + jh * 4) * kLanes + lane) * 4u;
+        const uint32_t coef_off = (uint32_t)kTcOperandBytes + (uint32_t)((q * kTcJW + jh * JPW) * kLanes + lane) * 4u;
         int s = 0;
         uint32_t sph = 0;
+        if (MODE == kModeAUniform) {
+            if (n_i > 0) {
+                mbar_wait(tmem_full, 0);
+                tc_fence_after();
+                float uh[NC];
+                tmem_ld<NC>(lane_base, uh);
+#pragma unroll
+                for (int jj = 0; jj < JPW; ++jj)
+#pragma unroll
+                    for (int d = 0; d < 16; ++d) acc[jj][d] = uh[jj * 16 + d];
+            }
+        } else
         for (int n = 0; n < n_i; ++n) {
             const int t = n & (kTcAccum - 1);
             const int i = i_begin + n;
-            float cc[4] = {0.f, 0.f, 0.f, 0.f};
+            float cc[JPW];
+#pragma unroll
+            for (int jj = 0; jj < JPW; ++jj) cc[jj] = 0.f;
             if (MODE == kModeA) {
                 mbar_wait(smem_full + 8 * s, sph);               // the bulk copies of stage s have landed
                 if (tvalid) {
                     const uint32_t ca = stages + (uint32_t)s * kTcStageBytes + coef_off;
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
+                    for (int jj = 0; jj < JPW; ++jj)
                         if (j0 + jj < p.C) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cc[jj]) : "r"(ca + jj * 128) : "memory");
                 }
             }
-            mbar_wait(tmem_full + 8 * t, (n >> 2) & 1);
+            mbar_wait(tmem_full + 8 * t, (n >> kTcAccumLog2) & 1);
             tc_fence_after();
-            float uh[64];
-            tmem_ld64(lane_base + (uint32_t)(t * kTcN), uh);
+            float uh[NC];
+            tmem_ld<NC>(lane_base + (uint32_t)(t * kTcN), uh);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * t);  // accumulator t may be overwritten
             if (MODE == kModeL) {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < JPW; ++jj) {
                     float dot = 0.f;
 #pragma unroll
                     for (int d = 0; d < 16; ++d) dot = fmaf(uh[jj * 16 + d], acc[jj][d], dot);
-                    if (tvalid && j0 + jj < p.C) p.out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = dot;
+                    if (tvalid && j0 + jj < p.C && !(p.dbg & 1)) p.out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = dot;
                 }
             } else {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const float f = (MODE == kModeA) ? cc[jj] : 1.f;
+                for (int jj = 0; jj < JPW; ++jj) {
+                    const float f = cc[jj];
 #pragma unroll
-                    for (int d = 0; d < 16; ++d) acc[jj][d] = fmaf(f, uh[jj * 16 + d], acc[jj][d]);
+                    for (int d = 0; d < 16; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f, f, uh[jj * 16 + d], uh[jj * 16 + d + 1]);
                 }
             }
             if (MODE == kModeA) {
@@ -371,7 +447,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
         }
         if (MODE != kModeL && tvalid) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+            for (int jj = 0; jj < JPW; ++jj)
                 if (j0 + jj < p.C) {
 #pragma unroll
                     for (int dq = 0; dq < 4; ++dq)
@@ -381,9 +457,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
         }
     }
 
+role_done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kTcEpiWarps + kTcIssuers) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
@@ -392,6 +469,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 }  // namespace
 
 int g_tc_stages = 10;
+int g_tc_dbg = 0;
 
 size_t tc_ua_floats(int B, int N) { return (size_t)cdiv(B > 0 ? B : 1, 128) * N * 2048; }
 size_t tc_wb_floats(int N, int C) { return (size_t)N * cdiv(C, kTcJW) * 2048; }
@@ -416,6 +494,7 @@ int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* 
     PassTcParams tp{};
     tp.ua = ua; tp.wb = wb; tp.coef = pp.coef; tp.X = pp.X; tp.out = pp.out;
     tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, kTcJW); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
+    tp.dbg = g_tc_dbg;
     tp.ns = g_tc_stages < 2 ? 2 : g_tc_stages > kTcMaxStages ? kTcMaxStages : g_tc_stages;
     while ((size_t)tp.ns * tc_stage_bytes(mode) + 512 > 227 * 1024) --tp.ns;      // 227 KB of dynamic smem per CTA
     const size_t smem = (size_t)tp.ns * tc_stage_bytes(mode) + 512;
