@@ -79,15 +79,26 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     while (spt > 1 && p.nbt < spt) spt >>= 1;
     p.SPT = spt;
     p.ntg = cdiv(p.nbt, p.SPT);
-    // split the i range until there are ~4 CTAs per SM worth of work
-    int is = g_tune_isplit > 0 ? g_tune_isplit : cdiv(4 * 148, (long)p.JG * p.ntg);
+    p.use_tc = g_tune_tc != 0 && D == 16 && C >= 4;
+    // split the i range until the grid fills the machine: the FMA kernel wants ~4 CTAs per SM, the tcgen05
+    // kernel owns an SM (all of TMEM), so one wave of its CTAs (128-sample quads x 8-capsule groups) is enough
+    const long ctas = p.use_tc ? (long)cdiv(C, 8) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
+    int is = g_tune_isplit > 0 ? g_tune_isplit : cdiv(4 * 148, ctas);
+    if (g_tune_isplit <= 0 && p.use_tc) {
+        // smallest split count (<= 32) whose grid wastes the least of its last wave of 148 CTAs
+        double best = -1.0;
+        for (int cand = 1; cand <= 32; ++cand) {
+            const long grid = ctas * cand;
+            const double eff = (double)grid / (double)(((grid + 147) / 148) * 148);
+            if (eff > best + 0.05) { best = eff; is = cand; }
+        }
+    }
     const int max_is = cdiv(N, kPassIC);
     if (is > max_is) is = max_is;
     if (is > 64) is = 64;
     if (is < 1) is = 1;
     p.i_per_split = cdiv(cdiv(N, is), kPassIC) * kPassIC;
     p.IS = cdiv(N, p.i_per_split);
-    p.use_tc = g_tune_tc != 0 && D == 16 && C >= 4;
     p.xs = round64((size_t)p.nbt * C * p.DP * 32);
     p.cs = round64((size_t)p.nbt * N * C * 32);
     p.us = round64((size_t)p.nbt * N * K * 32);

@@ -52,6 +52,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// two fp32 FMAs in one instruction (Blackwell FFMA2): d = a * b + d on a register pair
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    uint64_t a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
 // c += a * b with a (4 regs) and b (2 regs) given in fp32; 3xTF32
 __device__ __forceinline__ void mma3(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
     const uint32_t a0 = __float_as_uint(a[0]), a1 = __float_as_uint(a[1]), a2 = __float_as_uint(a[2]), a3 = __float_as_uint(a[3]);
@@ -170,14 +179,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
     }
 
     float* Gw = Gs + warp * 32 * GS;
-    // slot of this warp's coefficient m inside a stage (only non-constant terms are staged, in order)
-    int cslot[M];
-    float cconst[M];
-    {
-        int n = 0;
-#pragma unroll
-        for (int m = 0; m < M; ++m) { cslot[m] = p.coef[m] != nullptr ? n++ : -1; cconst[m] = p.cconst[m]; }
-    }
+    const float cconst0 = p.cconst[0];                      // term 0: the uniform coupling 1/C of iteration 0
     int sq = 0;                                             // ring position of the current unit
     uint32_t sph = 0;
     for (int tile = 0; tile < p.nbt; ++tile) {
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
 #pragma unroll
                 for (int dq = 0; dq < 4; ++dq) {
                     const float4 x = ldg4(p.X[m] + ((((size_t)tile * p.C + j) * 4 + dq) * kLanes + lane) * 4);
-                    xr[m][dq * 4 + 0] = x.x; xr[m][dq * 4 + 1] = x.y; xr[m][dq * 4 + 2] = x.z; xr[m][dq * 4 + 3] = x.w;
+                    const float f = (m == 0) ? cconst0 : 1.f;
+                    xr[m][dq * 4 + 0] = x.x * f; xr[m][dq * 4 + 1] = x.y * f; xr[m][dq * 4 + 2] = x.z * f; xr[m][dq * 4 + 3] = x.w * f;
                 }
         }
         for (int ib = 0; ib < IT; ib += DUB) {
@@ -201,12 +204,15 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                 const float* stg = ring + sq * SF;          // this unit's stage: [u: kq][32][4] then coefficient rows
                 if (il < ni) mbar_wait(bar_full + 8 * sq, sph);
                 if (jvalid && il < ni) {
+                    // term 0 has the constant coupling 1/C (already folded into xr[0] at tile load); terms 1..M-1 are
+                    // the staged coefficient rows, in order (caps_route_backward builds the list that way)
                     float G[16];
 #pragma unroll
-                    for (int d = 0; d < 16; ++d) G[d] = 0.f;
+                    for (int d = 0; d < 16; ++d) G[d] = xr[0][d];
+                    const float* crow = stg + 256 + warp * 32 + lane;
 #pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        const float al = cslot[m] >= 0 ? stg[256 + (cslot[m] * JW + warp) * 32 + lane] : cconst[m];
+                    for (int m = 1; m < M; ++m) {
+                        const float al = crow[(m - 1) * JW * 32];
 #pragma unroll
                         for (int d = 0; d < 16; ++d) G[d] = fmaf(al, xr[m][d], G[d]);
                     }
