@@ -302,9 +302,18 @@ def main_gpu(args, rank, world, device):
         dom, dom_ms, dom_bytes, dom_flops, dom_n = 'k_pass_tc (u_hat sweep, tcgen05 3xTF32)', ms_pass / max(n_pass, 1), pass_bytes, pass_flops, n_pass
         dom_share = ms_pass / ms_prof
     ach_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+    # measured DRAM traffic of that kernel (one `ncu --set full` capture, committed under profiles/), per launch
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))
+        if tj.get('batch') == B and tj.get('n_nodes') == N:
+            key = 'k_grad_mma<5>' if dom.startswith('k_grad') else 'k_pass_tc<1>'
+            traffic = tj['kernels'][key]['dram_bytes_per_launch']
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'kernel': '%s; %d launches/step' % (dom, dom_n // args.steps),
                 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
-                'traffic': None, 'peak_source': hbm_src, 'share_of_step': dom_share,
+                'traffic': traffic, 'peak_source': hbm_src, 'share_of_step': dom_share,
                 'algorithmic_tflops': dom_flops / (dom_ms * 1e-3) / 1e12,
                 'note': 'neither HBM nor the dense tensor peak binds this kernel: the contraction is K=8 wide and needs '
                         'fp32-grade accuracy (3xTF32), so the limit is shared-memory / issue bandwidth; see DESIGN.md section 5'}
