@@ -29,8 +29,9 @@ namespace {
 
 constexpr int kGmIT = 8;          // input capsules per CTA
 constexpr int kGmJW = 8;          // warps = output capsules per CTA
-constexpr int kGmDub = 4;         // capsules per du reduction round
-constexpr int kGmStages = 8;      // operand ring depth (units in flight per CTA)
+constexpr int kGmDub = 8;         // capsules per du reduction round
+// operand ring depth (units in flight per CTA): what fits next to the 180 KB of fixed tiles
+__host__ __device__ constexpr int gm_stages(int M) { return M <= 7 ? 6 : 5; }
 constexpr int kGmGStride = 20;    // floats per sample row of the G tile: 16-byte stores and the du fragment reads are
                                   // bank-conflict free, the dW fragment reads are 2-way on half their lanes
 
@@ -95,14 +96,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // grid = (ceil(N/8), ceil(C/8)); block = 288 (8 consumer warps + 1 producer warp).  K = 8, D = 16 only.
 //
 // The per-(b,i) operands -- the u tile and the 2R-2 coefficient rows of the CTA's 8 capsules -- are
-// streamed into a shared-memory ring by cp.async.bulk, kGmStages units ahead.  With plain (even
+// streamed into a shared-memory ring by cp.async.bulk, gm_stages(M) units ahead.  With plain (even
 // register-prefetched) loads the kernel ran at exactly one loaded-HBM latency (~1750 cycles) per unit
 // whatever the math did (11 ms with ALL the math removed): 8 warps with one unit of loads in flight each
 // is far too little memory-level parallelism.
 template <int M>
 __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
     constexpr int IT = kGmIT, JW = kGmJW, DUB = kGmDub, GS = kGmGStride, NT = 32 * JW;     // NT: consumer threads
-    constexpr int NS = kGmStages, SF = 256 + (M - 1) * JW * 32;       // stage: u tile + up to M-1 coefficient rows
+    constexpr int NS = gm_stages(M), SF = 256 + (M - 1) * JW * 32;       // stage: u tile + up to M-1 coefficient rows
     extern __shared__ __align__(16) float smem[];
     float* Wfrag = smem;                                   // [IT][JW][ks 2][hl 2][32 lanes][2]
     float* dWsm = Wfrag + IT * JW * 256;                   // [IT][JW][32 lanes][4]
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
 template <int M>
 int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     const size_t smem = ((size_t)kGmIT * kGmJW * 256 + kGmIT * kGmJW * 128 + kGmJW * 32 * kGmGStride + kGmJW * kGmDub * 256 +
-                         (size_t)kGmStages * (256 + (M - 1) * kGmJW * 32)) * sizeof(float) + 16 * kGmStages;
+                         (size_t)gm_stages(M) * (256 + (M - 1) * kGmJW * 32)) * sizeof(float) + 16 * gm_stages(M);
     auto kern = k_grad_mma<M>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, kGmJW)), block(32 * kGmJW + 32);
