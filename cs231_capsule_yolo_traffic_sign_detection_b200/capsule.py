@@ -226,7 +226,7 @@ class HostStep:
         self.scratch = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
         self.loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
         self.h2d_bytes = B * N * K * 4 + B * 8
-        self.d2h_bytes = 4
+        self.d2h_bytes = 4 if B < 2048 else 12          # one loss term per micro-batch
 
     def __call__(self, u_host, y_host, W_dev, dW_dev, v_host=None, du_host=None):
         B, N, C, K, D, R = self.dims

@@ -27,6 +27,7 @@ using namespace caps;
 int g_tune_spt = 0;      // 0 = auto
 int g_tune_isplit = 0;   // 0 = auto
 int g_tune_gradmma = 1;  // 1 = mma.sync gradient kernel where it applies (D == 16, C >= 7)
+int g_tune_hostmb = 0;   // caps_route_step_host: 0 = auto (3 micro-batches from B >= 2048), 1 = single batch
 int g_tune_tc = 1;       // 1 = use the tcgen05 pass kernel where it applies, 0 = FFMA kernel only
 
 // ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
@@ -218,6 +219,7 @@ int caps_set_tuning(const char* name, int value) {
     if (!strcmp(name, "tcdbg")) { g_tc_dbg = value; return 0; }
     if (!strcmp(name, "tcstages")) { if (value < 2 || value > 12) return fail(CAPS_E_BADARG, "tcstages must be in [2,12]"); g_tc_stages = value; return 0; }
     if (!strcmp(name, "gradmma")) { g_tune_gradmma = value != 0; return 0; }
+    if (!strcmp(name, "hostmb")) { g_tune_hostmb = value; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
         if (value < 0 || value > 64) return fail(CAPS_E_BADARG, "isplit must be in [0,64]");
@@ -422,11 +424,25 @@ int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, 
 }
 
 // ---- host-buffer step ------------------------------------------------------------------------
+// The batch is cut into up to three micro-batches (B/8, 3B/8, B/2, multiples of 128) so that the
+// host->device copy of micro-batch m+1 (on an internal copy stream) runs under the kernels of
+// micro-batch m; the first one is small so the pipeline fills quickly.  dW is summed over the
+// micro-batches in a fixed order (bit-reproducible); loss terms are summed on the host.
 namespace {
-struct HostStepLayout { size_t o_u, o_y, o_v, o_du, o_loss, o_lscr, o_ws, total; };
+constexpr int kHostMaxMb = 3;
+struct HostStepLayout { size_t o_u, o_y, o_v, o_du, o_loss, o_lscr, o_dwt, o_ws, total; int nmb; int mb[kHostMaxMb]; };
 bool host_step_layout(HostStepLayout& L, int B, int N, int C, int K, int D, int R) {
-    const size_t wsb = caps_route_workspace_bytes(B, N, C, K, D, R, 1);
-    if (wsb == 0) return false;
+    L.nmb = 1; L.mb[0] = B;
+    if (g_tune_hostmb != 1 && B >= 2048) {
+        const int c0 = std::max(128, (B / 8) / 128 * 128), c1 = std::max(128, (3 * (B / 8)) / 128 * 128);
+        L.nmb = 3; L.mb[0] = c0; L.mb[1] = c1; L.mb[2] = B - c0 - c1;
+    }
+    size_t wsb = 0;
+    for (int m = 0; m < L.nmb; ++m) {
+        const size_t w = caps_route_workspace_bytes(L.mb[m], N, C, K, D, R, 1);
+        if (w == 0) return false;
+        wsb = std::max(wsb, w);
+    }
     auto r256 = [](size_t n) { return (n + 255) & ~(size_t)255; };
     size_t o = 0;
     L.o_u = o; o += r256((size_t)B * N * K * 4);
@@ -435,10 +451,13 @@ bool host_step_layout(HostStepLayout& L, int B, int N, int C, int K, int D, int 
     L.o_du = o; o += r256((size_t)B * N * K * 4);
     L.o_loss = o; o += 256;
     L.o_lscr = o; o += r256(CAPS_MARGIN_SCRATCH_FLOATS * 4);
+    L.o_dwt = o; o += L.nmb > 1 ? r256((size_t)N * C * K * D * 4) : 0;
     L.o_ws = o; o += r256(wsb);
     L.total = o;
     return true;
 }
+cudaStream_t g_copy_stream = nullptr;
+cudaEvent_t g_copy_ev[kHostMaxMb + 1];
 }  // namespace
 
 size_t caps_route_step_host_scratch_bytes(int B, int N, int C, int K, int D, int R) {
@@ -461,21 +480,50 @@ int caps_route_step_host(const float* u_host, const int64_t* y_host, const float
     float* v_d = reinterpret_cast<float*>(base + L.o_v);
     float* du_d = reinterpret_cast<float*>(base + L.o_du);
     float* loss_d = reinterpret_cast<float*>(base + L.o_loss);
+    float* dwt = reinterpret_cast<float*>(base + L.o_dwt);
     void* ws = base + L.o_ws;
     const size_t wsb = L.total - L.o_ws;
-    CUDA_TRY(cudaMemcpyAsync(u_d, u_host, (size_t)B * N * K * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(y_d, y_host, (size_t)B * 8, cudaMemcpyHostToDevice, st));
-    int rc;
-    if ((rc = caps_route_forward(u_d, W_dev, v_d, nullptr, ws, wsb, B, N, C, K, D, R, 1, stream))) return rc;
+    const size_t row_u = (size_t)N * K, row_v = (size_t)C * D;
     const float scale = 1.f / (float)B;
-    if ((rc = caps_margin_loss(v_d, y_d, scale, loss_d, nullptr, reinterpret_cast<float*>(base + L.o_lscr), B, C, D, stream))) return rc;
-    if ((rc = caps_route_backward(u_d, W_dev, nullptr, y_d, scale, nullptr, du_host ? du_d : nullptr, dW_dev, ws, wsb,
-                                  B, N, C, K, D, R, stream)))
-        return rc;
-    CUDA_TRY(cudaMemcpyAsync(loss_host, loss_d, 4, cudaMemcpyDeviceToHost, st));
+    cudaStream_t cs = st;
+    if (L.nmb > 1) {
+        if (!g_copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+            for (auto& e : g_copy_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        cs = g_copy_stream;
+        // the copy stream may only overwrite u/y once everything already queued on `st` is done
+        CUDA_TRY(cudaEventRecord(g_copy_ev[kHostMaxMb], st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, g_copy_ev[kHostMaxMb], 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(y_d, y_host, (size_t)B * 8, cudaMemcpyHostToDevice, cs));
+    for (int m = 0, b0 = 0; m < L.nmb; b0 += L.mb[m], ++m) {
+        CUDA_TRY(cudaMemcpyAsync(u_d + b0 * row_u, u_host + b0 * row_u, L.mb[m] * row_u * 4, cudaMemcpyHostToDevice, cs));
+        if (L.nmb > 1) CUDA_TRY(cudaEventRecord(g_copy_ev[m], cs));
+    }
+    int rc;
+    for (int m = 0, b0 = 0; m < L.nmb; b0 += L.mb[m], ++m) {
+        const int Bm = L.mb[m];
+        if (L.nmb > 1) CUDA_TRY(cudaStreamWaitEvent(st, g_copy_ev[m], 0));
+        float* dW_m = m == 0 ? dW_dev : dwt;
+        if ((rc = caps_route_forward(u_d + b0 * row_u, W_dev, v_d + b0 * row_v, nullptr, ws, wsb, Bm, N, C, K, D, R, 1, stream))) return rc;
+        if ((rc = caps_margin_loss(v_d + b0 * row_v, y_d + b0, scale, loss_d + m, nullptr, reinterpret_cast<float*>(base + L.o_lscr), Bm, C, D, stream))) return rc;
+        if ((rc = caps_route_backward(u_d + b0 * row_u, W_dev, nullptr, y_d + b0, scale, nullptr, du_host ? du_d + b0 * row_u : nullptr, dW_m,
+                                      ws, wsb, Bm, N, C, K, D, R, stream)))
+            return rc;
+        if (m > 0) {
+            const long n = (long)N * C * K * D;
+            LaunchScope ls_(kcOther, st);
+            k_add_inplace<<<cdiv(n, 256), 256, 0, st>>>(dW_dev, dwt, n);
+            LAUNCH_CHECK();
+        }
+    }
+    float loss_parts[kHostMaxMb] = {0.f, 0.f, 0.f};
+    CUDA_TRY(cudaMemcpyAsync(L.nmb > 1 ? loss_parts : loss_host, loss_d, 4 * L.nmb, cudaMemcpyDeviceToHost, st));
     if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, v_d, (size_t)B * C * D * 4, cudaMemcpyDeviceToHost, st));
     if (du_host) CUDA_TRY(cudaMemcpyAsync(du_host, du_d, (size_t)B * N * K * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (L.nmb > 1) *loss_host = (loss_parts[0] + loss_parts[1]) + loss_parts[2];
     return 0;
 }
 

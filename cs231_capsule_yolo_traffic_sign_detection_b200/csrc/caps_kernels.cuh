@@ -506,6 +506,11 @@ static __global__ void k_fill(float* __restrict__ p, float val, long n) {
     if (idx < n) p[idx] = val;
 }
 
+static __global__ void k_add_inplace(float* __restrict__ acc, const float* __restrict__ x, long n) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) acc[idx] += x[idx];
+}
+
 // ---------------------------------------------------------------------------------------------
 // final backward pass: G_bij = sum_m alpha^m_bij X^m_bj ;  dW_ij = sum_b u_bi (x) G_bij ;
 //                      du_bi = sum_j W_ij G_bij

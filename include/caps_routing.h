@@ -96,7 +96,10 @@ int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, 
  * loss, fused backward, and copies loss (and, if non-NULL, v / du / dW) device->host, all on
  * `stream`, then synchronises that stream.  u_host/y_host/..._host are HOST pointers (pinned for
  * speed).  W_dev/dW_dev stay on the device (weights live there).  dev_scratch is a device
- * buffer of >= caps_route_step_host_scratch_bytes(...) bytes. */
+ * buffer of >= caps_route_step_host_scratch_bytes(...) bytes.  From B >= 2048 the batch is cut
+ * into three micro-batches (B/8, 3B/8, B/2) whose copies run on an internal stream under the
+ * previous micro-batch's kernels; dW is their sum in a fixed order (caps_set_tuning("hostmb", 1)
+ * forces a single batch; the scratch size depends on the setting at sizing time). */
 size_t caps_route_step_host_scratch_bytes(int B, int N, int C, int K, int D, int R);
 int caps_route_step_host(const float* u_host, const int64_t* y_host, const float* W_dev,
                          float* loss_host, float* v_host, float* du_host, float* dW_dev,
@@ -122,6 +125,7 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
  *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
  *                 (D == 16, C >= 7); 0: fp32-FMA gradient kernel everywhere
+ *   name = "hostmb" caps_route_step_host micro-batching: 0 (default) auto, 1 single batch
  *   name = "profile" 1: bracket every launch with CUDA events (see caps_profile_collect)
  * Returns 0, or CAPS_E_BADARG for an unknown name/value.  Meant for benchmarks and tests. */
 int caps_set_tuning(const char* name, int value);

@@ -258,6 +258,42 @@ def test_host_step_matches_device_path(capsb):
     assert np.array_equal(dWd.cpu().numpy(), ref['dW'])
 
 
+def test_host_step_micro_batches(capsb):
+    """From B >= 2048 the host step pipelines three micro-batches (copy under compute); v / du are
+    per-sample so they keep the device path's bits, dW and the loss are re-associated sums."""
+    from oracle import routing_np as onp
+    from cs231_capsule_yolo_traffic_sign_detection_b200 import _cabi
+    B, N, C, K, D, R = 2048 + 128, 40, 10, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=9)
+    dev = torch.device('cuda')
+    Wd = torch.from_numpy(W).to(dev)
+    uh = torch.from_numpy(u).pin_memory()
+    yh = torch.from_numpy(y).pin_memory()
+    outs = []
+    for hostmb in (1, 0):
+        _cabi.set_tuning('hostmb', hostmb)
+        _cabi.set_tuning('isplit', 4)
+        try:
+            step = capsb.HostStep(B, N, C, K, D, R)
+            dWd = torch.empty_like(Wd)
+            vh = torch.empty(B, C, D).pin_memory()
+            duh = torch.empty(B, N, K).pin_memory()
+            loss = float(step(uh, yh, Wd, dWd, v_host=vh, du_host=duh)[0])
+            outs.append((loss, vh.numpy().copy(), duh.numpy().copy(), dWd.cpu().numpy()))
+            if hostmb == 0:      # twice the same call: same bits (fixed summation order over micro-batches)
+                dW4 = torch.empty_like(Wd)
+                step(uh, yh, Wd, dW4)
+                assert np.array_equal(dW4.cpu().numpy(), outs[-1][3])
+        finally:
+            _cabi.set_tuning('hostmb', 0)
+            _cabi.set_tuning('isplit', 0)
+    (l1, v1, du1, dW1), (l3, v3, du3, dW3) = outs
+    assert abs(l1 - l3) < 1e-6 * max(1.0, abs(l1))
+    assert np.array_equal(v1, v3)
+    assert np.array_equal(du1, du3)
+    assert rel_err(dW3, dW1) < 1e-5
+
+
 def test_squash_kernel(capsb):
     from oracle import routing_np as onp
     dev = torch.device('cuda')
