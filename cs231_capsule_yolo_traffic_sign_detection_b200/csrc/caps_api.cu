@@ -141,11 +141,11 @@ int launch_squash(const Plan& pl, const float* part, float scale, float* s_out, 
 }
 
 int launch_dsquash(const Plan& pl, const float* part, const float* grad_v, const int64_t* y, float mscale,
-                   const float* lgrad, const float* v_last, const float* s_in, float* ds_out, cudaStream_t st) {
+                   const float* lgrad, const float* v_last, const float* s_in, float* ds_out, float out_scale, cudaStream_t st) {
     const long n = (long)pl.nbt * pl.C * 32;
     LaunchScope ls_(kcSquash, st);
     DISPATCH_DP(pl, (k_dsquash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, pl.IS, pl.xs, grad_v, y, mscale, lgrad, v_last,
-                                                                   s_in, ds_out, pl.B, pl.C, pl.D, pl.nbt)));
+                                                                   s_in, ds_out, out_scale, pl.B, pl.C, pl.D, pl.nbt)));
     LAUNCH_CHECK();
     return 0;
 }
@@ -334,9 +334,13 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     float* tmp = w + pl.o_tmp;
     const int Re = pl.Reff;
     int rc;
+    // The mma gradient kernel wants ds^0 pre-multiplied by iteration 0's uniform coupling 1/C (ds^0 has no other
+    // reader); the FMA kernel multiplies by cconst[0] itself.  Same fp32 product either way.
+    const bool grad_mma = g_tune_gradmma && pl.DP == 16 && pl.D == 16 && pl.JW == 8;
+    const float ds0_scale = grad_mma ? 1.f / (float)C : 1.f;
     // top: dv = grad_v + margin gradient ; ds^{R-1}
     if ((rc = launch_dsquash(pl, nullptr, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),
-                             w + pl.o_s + pl.xs * (Re - 1), w + pl.o_ds + pl.xs * (Re - 1), st)))
+                             w + pl.o_s + pl.xs * (Re - 1), w + pl.o_ds + pl.xs * (Re - 1), Re == 1 ? ds0_scale : 1.f, st)))
         return rc;
     for (int r = Re - 1; r >= 1; --r) {
         const float* c_r = w + pl.o_c + pl.cs * (r - 1);
@@ -358,7 +362,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
         if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
         if ((rc = launch_dsquash(pl, part, nullptr, nullptr, 0.f, nullptr, nullptr, w + pl.o_s + pl.xs * (r - 1),
-                                 w + pl.o_ds + pl.xs * (r - 1), st)))
+                                 w + pl.o_ds + pl.xs * (r - 1), r == 1 ? ds0_scale : 1.f, st)))
             return rc;
     }
     GradParams gp{};
@@ -367,7 +371,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     int m = 0;
     for (int r = 0; r < Re; ++r) {                                          // c^r (x) ds^r
         gp.coef[m] = (r == 0) ? nullptr : w + pl.o_c + pl.cs * (r - 1);
-        gp.cconst[m] = 1.f / (float)C;
+        gp.cconst[m] = (r == 0 && grad_mma) ? 1.f : 1.f / (float)C;
         gp.X[m] = w + pl.o_ds + pl.xs * r;
         ++m;
     }
@@ -379,7 +383,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     }
     {
         LaunchScope ls_(kcGrad, st);
-        rc = (g_tune_gradmma && pl.DP == 16 && pl.D == 16 && pl.JW == 8) ? launch_grad_mma(pl, gp, st) : launch_grad(pl, gp, st);
+        rc = grad_mma ? launch_grad_mma(pl, gp, st) : launch_grad(pl, gp, st);
     }
     if (rc) return rc;
     if (du != nullptr) {

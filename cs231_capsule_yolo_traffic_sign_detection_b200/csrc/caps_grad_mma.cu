@@ -180,21 +180,27 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
     }
 
     float* Gw = Gs + warp * 32 * GS;
-    const float cconst0 = p.cconst[0];                      // term 0: the uniform coupling 1/C of iteration 0
     int sq = 0;                                             // ring position of the current unit
     uint32_t sph = 0;
+    // X^m of (tile, j): 16 floats per term and lane; term 0 arrives pre-multiplied by its constant coupling 1/C
+    // (caps_route_backward has k_dsquash do it), so nothing depends on the loads until the next unit.  The loads
+    // for tile + 1 are issued in the middle of the tile's last unit (right after its G is built, when xr is dead)
+    // so that their L2 latency hides under that unit's MMA phase instead of stalling all 8 warps once per tile.
+    float xr[M][16];
+    auto load_x = [&](int tile) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int dq = 0; dq < 4; ++dq) {
+                // volatile + "memory": must stay below the warp barrier it follows, or ptxas hoists it above the G
+                // FMAs, needs a second register set for X and spills
+                asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(xr[m][dq * 4 + 0]), "=f"(xr[m][dq * 4 + 1]), "=f"(xr[m][dq * 4 + 2]), "=f"(xr[m][dq * 4 + 3])
+                             : "l"(p.X[m] + ((((size_t)tile * p.C + j) * 4 + dq) * kLanes + lane) * 4) : "memory");
+            }
+    };
+    if (jvalid) load_x(0);
     for (int tile = 0; tile < p.nbt; ++tile) {
-        float xr[M][16];
-        if (jvalid) {
-#pragma unroll
-            for (int m = 0; m < M; ++m)
-#pragma unroll
-                for (int dq = 0; dq < 4; ++dq) {
-                    const float4 x = ldg4(p.X[m] + ((((size_t)tile * p.C + j) * 4 + dq) * kLanes + lane) * 4);
-                    const float f = (m == 0) ? cconst0 : 1.f;
-                    xr[m][dq * 4 + 0] = x.x * f; xr[m][dq * 4 + 1] = x.y * f; xr[m][dq * 4 + 2] = x.z * f; xr[m][dq * 4 + 3] = x.w * f;
-                }
-        }
         for (int ib = 0; ib < IT; ib += DUB) {
 #pragma unroll 1
             for (int ii = 0; ii < DUB; ++ii) {
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                 const float* stg = ring + sq * SF;          // this unit's stage: [u: kq][32][4] then coefficient rows
                 if (il < ni) mbar_wait(bar_full + 8 * sq, sph);
                 if (jvalid && il < ni) {
-                    // term 0 has the constant coupling 1/C (already folded into xr[0] at tile load); terms 1..M-1 are
+                    // term 0 has the constant coupling 1/C (already folded into X^0 by its producer); terms 1..M-1 are
                     // the staged coefficient rows, in order (caps_route_backward builds the list that way)
                     float G[16];
 #pragma unroll
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                     for (int dq = 0; dq < 4; ++dq)
                         st4(Gw + lane * GS + dq * 4, make_float4(G[dq * 4], G[dq * 4 + 1], G[dq * 4 + 2], G[dq * 4 + 3]));
                     __syncwarp();
+                    if (il == ni - 1 && tile + 1 < p.nbt) load_x(tile + 1);
                     // ---- dW[d][k] += sum_b G[b][d] u[b][k] : 4 chunks of 8 samples, two accumulators
                     float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll

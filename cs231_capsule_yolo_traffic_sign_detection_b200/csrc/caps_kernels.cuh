@@ -333,11 +333,12 @@ __global__ void k_squash(const float* __restrict__ part, int IS, size_t xsize, f
 // ds = squash_bwd(s, dv) with
 //   dv = sum_is part[is]                                   (inner iterations), or
 //   dv = grad_v[b][j][:] + margin_scale * d margin / d v   (top: part == nullptr)
+// ds_out = out_scale * ds.
 template <int DP>
 __global__ void k_dsquash(const float* __restrict__ part, int IS, size_t xsize,
                           const float* __restrict__ grad_v, const int64_t* __restrict__ y, float margin_scale,
                           const float* __restrict__ loss_grad, const float* __restrict__ v_last, const float* __restrict__ s_in,
-                          float* __restrict__ ds_out, int B, int C, int D, int nbt) {
+                          float* __restrict__ ds_out, float out_scale, int B, int C, int D, int nbt) {
     constexpr int D4 = DP / 4;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)nbt * C * kLanes) return;
@@ -390,6 +391,8 @@ __global__ void k_dsquash(const float* __restrict__ part, int IS, size_t xsize,
     }
     if (b < B) {
         squash_bwd_vec<DP>(s, dv, ds);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) ds[d] *= out_scale;     // 1, or the uniform coupling 1/C of iteration 0 (see caps_route_backward)
     } else {
 #pragma unroll
         for (int d = 0; d < DP; ++d) ds[d] = 0.f;
