@@ -219,6 +219,11 @@ int caps_set_tuning(const char* name, int value) {
     if (!strcmp(name, "tcdbg")) { g_tc_dbg = value; return 0; }
     if (!strcmp(name, "tcstages")) { if (value < 2 || value > 12) return fail(CAPS_E_BADARG, "tcstages must be in [2,12]"); g_tc_stages = value; return 0; }
     if (!strcmp(name, "gradmma")) { g_tune_gradmma = value != 0; return 0; }
+    if (!strcmp(name, "gradjw")) {
+        if (value != 0 && value != 8 && value != 11) return fail(CAPS_E_BADARG, "gradjw must be 0, 8 or 11");
+        g_grad_jw = value;
+        return 0;
+    }
     if (!strcmp(name, "hostmb")) { g_tune_hostmb = value; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
@@ -388,7 +393,8 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     if (rc) return rc;
     if (du != nullptr) {
         const long n = (long)pl.nbt * N * 32;
-        { LaunchScope ls_(kcReduceDu, st); k_reduce_du<8><<<cdiv(n, 128), 128, 0, st>>>(gp.du_part, pl.JG, du, B, N, pl.nbt); }
+        const int parts = grad_mma ? cdiv(C, grad_mma_jw(pl)) : pl.JG;
+        { LaunchScope ls_(kcReduceDu, st); k_reduce_du<8><<<cdiv(n, 128), 128, 0, st>>>(gp.du_part, parts, du, B, N, pl.nbt); }
         LAUNCH_CHECK();
     }
     return 0;

@@ -28,12 +28,25 @@ namespace caps {
 namespace {
 
 constexpr int kGmIT = 8;          // input capsules per CTA
-constexpr int kGmJW = 8;          // warps = output capsules per CTA
-constexpr int kGmDub = 8;         // capsules per du reduction round
-// operand ring depth (units in flight per CTA): what fits next to the 180 KB of fixed tiles
-__host__ __device__ constexpr int gm_stages(int M) { return M <= 7 ? 6 : 5; }
-constexpr int kGmGStride = 20;    // floats per sample row of the G tile: 16-byte stores and the du fragment reads are
-                                  // bank-conflict free, the dW fragment reads are 2-way on half their lanes
+// Consumer warps (= output capsules) per CTA: 8 or 11.  11 + the producer warp = 384 threads is the most that still
+// leaves 168 registers per thread (X^m alone takes 16 M); three warps per scheduler instead of two hide more of the
+// LDS -> split -> HMMA chain, and C = 43 is 4 x 11 - 1.
+__host__ __device__ constexpr int gm_dub(int JW) { return JW == 8 ? 8 : 4; }          // input capsules per du reduction round
+__host__ __device__ constexpr int gm_stage_floats(int M, int JW) { return 272 + (M - 1) * JW * 32; }
+__host__ __device__ constexpr int gm_fixed_floats(int JW) {
+    return kGmIT * JW * 128 /* Wfrag */ + kGmIT * JW * 128 /* dWsm */ + JW * 32 * 16 /* Gs */ + JW * gm_dub(JW) * 256 /* dusm */;
+}
+// operand ring depth (units in flight per CTA): what fits next to the fixed tiles, at most 8
+__host__ __device__ constexpr int gm_stages(int M, int JW) {
+    int ns = (227 * 1024 - 256 - gm_fixed_floats(JW) * 4) / (gm_stage_floats(M, JW) * 4 + 16);
+    return ns > 8 ? 8 : ns;
+}
+// G tile of a warp: [32 samples][16 dims], no padding, with the 4-float column groups XOR-swizzled by sample bits 1
+// and 2:  float (b, d) lives at b * 16 + (d ^ gm_sigma(b)).  That makes all three access patterns bank-conflict free:
+// the 16-byte row stores (lane <-> b), the dW fragment reads (lane (g,t) <-> b = t, d = g) and the du fragment reads
+// (ldmatrix rows b = g, 16-byte chunks of d).  No linear row stride can do both fragment patterns at once.
+__device__ __forceinline__ int gm_sigma(int b) { return 8 * ((b >> 1) & 1) + 4 * ((b >> 2) & 1); }
+constexpr int kGmUSkew = 144;     // floats between the two k-halves of the staged u tile (128 + 16: halves 16 banks apart)
 
 __device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                  uint32_t b0, uint32_t b1) {
@@ -47,11 +60,6 @@ __device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], uint32_t a0, uin
 // lo) are ~2^-20 relative.
 __device__ __forceinline__ uint32_t tf32_lo(float x) {
     return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
-}
-// used once per CTA for the W fragments (round-to-nearest hi, exact lo)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // two fp32 FMAs in one instruction (Blackwell FFMA2): d = a * b + d on a register pair
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
@@ -100,16 +108,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // register-prefetched) loads the kernel ran at exactly one loaded-HBM latency (~1750 cycles) per unit
 // whatever the math did (11 ms with ALL the math removed): 8 warps with one unit of loads in flight each
 // is far too little memory-level parallelism.
-template <int M>
-__global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
-    constexpr int IT = kGmIT, JW = kGmJW, DUB = kGmDub, GS = kGmGStride, NT = 32 * JW;     // NT: consumer threads
-    constexpr int NS = gm_stages(M), SF = 256 + (M - 1) * JW * 32;       // stage: u tile + up to M-1 coefficient rows
+template <int M, int JW>
+__global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
+    constexpr int IT = kGmIT, DUB = gm_dub(JW), NT = 32 * JW;     // NT: consumer threads
+    constexpr int NS = gm_stages(M, JW), SF = gm_stage_floats(M, JW);    // stage: u tile + up to M-1 coefficient rows
+    static_assert(NS >= 3, "operand ring too shallow");
     extern __shared__ __align__(16) float smem[];
-    float* Wfrag = smem;                                   // [IT][JW][ks 2][hl 2][32 lanes][2]
-    float* dWsm = Wfrag + IT * JW * 256;                   // [IT][JW][32 lanes][4]
-    float* Gs = dWsm + IT * JW * 128;                      // [JW][32][GS]
-    float* dusm = Gs + JW * 32 * GS;                       // [JW][DUB][half 2][32 lanes][4]
-    float* ring = dusm + JW * DUB * 256;                   // [NS][ u tile [2][32][4] | coef rows [M-1][JW][32] ]
+    float* Wfrag = smem;                                   // [IT][JW][ks 2][32 lanes][2]
+    float* dWsm = Wfrag + IT * JW * 128;                   // [IT][JW][32 lanes][4]
+    float* Gs = dWsm + IT * JW * 128;                      // [JW][32][16] swizzled
+    float* dusm = Gs + JW * 32 * 16;                       // [JW][DUB][half 2][32 lanes][4]
+    float* ring = dusm + JW * DUB * 256;                   // [NS][ u tile [kq 2][32][4], halves kGmUSkew apart | coef rows [M-1][JW][32] ]
     const uint32_t bars = smem_u32(ring + NS * SF);        // full[NS], empty[NS]
     const uint32_t bar_full = bars, bar_empty = bars + 8 * NS;
 
@@ -132,12 +141,8 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
             w0 = __ldg(row + tt + 8 * ks);
             w1 = __ldg(row + tt + 4 + 8 * ks);
         }
-        uint32_t h0, l0, h1, l1;
-        split_tf32(w0, h0, l0);
-        split_tf32(w1, h1, l1);
-        float* dst = Wfrag + (size_t)((il * JW + w) * 2 + ks) * 128;
-        *reinterpret_cast<float2*>(dst + l * 2) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
-        *reinterpret_cast<float2*>(dst + 64 + l * 2) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+        // kept whole: the tensor core truncates its operands, so the "hi" half is w itself and lo = tf32_lo(w) at use
+        *reinterpret_cast<float2*>(Wfrag + (size_t)((il * JW + w) * 2 + ks) * 64 + l * 2) = make_float2(w0, w1);
     }
     for (int e = threadIdx.x; e < IT * JW * 128; e += blockDim.x) dWsm[e] = 0.f;
     if (threadIdx.x == 0) {
@@ -163,8 +168,10 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                     const uint32_t dst = smem_u32(ring + q * SF), bar = bar_full + 8 * q;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(txbytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst), "l"(p.ut + ti * 256), "r"(ubytes), "r"(bar) : "memory");
-                    uint32_t cd = dst + ubytes;
+                                 ::"r"(dst), "l"(p.ut + ti * 256), "r"(ubytes / 2), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst + kGmUSkew * 4), "l"(p.ut + ti * 256 + 128), "r"(ubytes / 2), "r"(bar) : "memory");
+                    uint32_t cd = dst + 272 * 4;
 #pragma unroll
                     for (int m = 0; m < M; ++m)
                         if (p.coef[m] != nullptr) {
@@ -179,7 +186,16 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
         return;                                             // the consumers synchronise among themselves (named barrier 1)
     }
 
-    float* Gw = Gs + warp * 32 * GS;
+    float* Gw = Gs + warp * 32 * 16;
+    // lane-invariant swizzled offsets into the G tile (floats)
+    const int st_sw = gm_sigma(lane) >> 2;                                   // row store: group dq goes to dq ^ st_sw
+    const int dwa0 = t * 16 + (g ^ gm_sigma(t));                             // dW A-fragment: (b = t, d = g); d + 8 is ^ 8
+    const int dwa2 = (t + 4) * 16 + (g ^ gm_sigma(t + 4));                   //                (b = t + 4, d = g)
+    // du A-fragment by ldmatrix.x4: this lane supplies the address of row (lane & 7) of matrix (lane >> 3):
+    // matrices 0/1 = samples +0 / +8 of dims 8 ks + 0..3, matrices 2/3 = the same samples, dims 8 ks + 4..7
+    const int lm_row = 8 * ((lane >> 3) & 1) + (lane & 7);
+    const uint32_t lm_a0 = smem_u32(Gw + lm_row * 16 + (((lane >> 4) * 4) ^ gm_sigma(lm_row)));     // ks = 0
+    const uint32_t lm_a1 = smem_u32(Gw + lm_row * 16 + (((lane >> 4) * 4 + 8) ^ gm_sigma(lm_row))); // ks = 1
     int sq = 0;                                             // ring position of the current unit
     uint32_t sph = 0;
     // X^m of (tile, j): 16 floats per term and lane; term 0 arrives pre-multiplied by its constant coupling 1/C
@@ -208,7 +224,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                 float duf[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) duf[e] = 0.f;
-                const float* stg = ring + sq * SF;          // this unit's stage: [u: kq][32][4] then coefficient rows
+                const float* stg = ring + sq * SF;          // this unit's stage: u tile, then coefficient rows
                 if (il < ni) mbar_wait(bar_full + 8 * sq, sph);
                 if (jvalid && il < ni) {
                     // term 0 has the constant coupling 1/C (already folded into X^0 by its producer); terms 1..M-1 are
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                     float G[16];
 #pragma unroll
                     for (int d = 0; d < 16; ++d) G[d] = xr[0][d];
-                    const float* crow = stg + 256 + warp * 32 + lane;
+                    const float* crow = stg + 272 + warp * 32 + lane;
 #pragma unroll
                     for (int m = 1; m < M; ++m) {
                         const float al = crow[(m - 1) * JW * 32];
@@ -226,18 +242,17 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                     __syncwarp();                                   // previous unit's fragment reads are done
 #pragma unroll
                     for (int dq = 0; dq < 4; ++dq)
-                        st4(Gw + lane * GS + dq * 4, make_float4(G[dq * 4], G[dq * 4 + 1], G[dq * 4 + 2], G[dq * 4 + 3]));
+                        st4(Gw + lane * 16 + ((dq ^ st_sw) * 4), make_float4(G[dq * 4], G[dq * 4 + 1], G[dq * 4 + 2], G[dq * 4 + 3]));
                     __syncwarp();
                     if (il == ni - 1 && tile + 1 < p.nbt) load_x(tile + 1);
                     // ---- dW[d][k] += sum_b G[b][d] u[b][k] : 4 chunks of 8 samples, two accumulators
                     float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float* gr0 = Gw + (8 * c + t) * GS;
-                        const float* gr1 = Gw + (8 * c + t + 4) * GS;
-                        const float a[4] = {gr0[g], gr0[g + 8], gr1[g], gr1[g + 8]};
-                        // u[b][k] straight out of the stage: (k >> 2) * 128 + b * 4 + (k & 3)
-                        const float* ub = stg + (g >> 2) * 128 + (8 * c + t) * 4 + (g & 3);
+                        const float* gc = Gw + c * 128;
+                        const float a[4] = {gc[dwa0], gc[dwa0 ^ 8], gc[dwa2], gc[dwa2 ^ 8]};
+                        // u[b][k] straight out of the stage: (k >> 2) * kGmUSkew + b * 4 + (k & 3)
+                        const float* ub = stg + (g >> 2) * kGmUSkew + (8 * c + t) * 4 + (g & 3);
                         const float b[2] = {ub[0], ub[16]};
                         if (c & 1) mma3(c1, a, b); else mma3(c0, a, b);
                     }
@@ -251,15 +266,14 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                         float cc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
-                            const float* gr0 = Gw + (16 * mt + g) * GS + 8 * ks;
-                            const float* gr1 = Gw + (16 * mt + g + 8) * GS + 8 * ks;
-                            const float av[4] = {gr0[t], gr1[t], gr0[t + 4], gr1[t + 4]};
                             uint32_t ah[4], al[4];
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3])
+                                         : "r"((ks ? lm_a1 : lm_a0) + mt * 1024) : "memory");
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) { ah[e] = __float_as_uint(av[e]); al[e] = tf32_lo(av[e]); }
-                            const float* wf = Wfrag + (size_t)((il * JW + warp) * 2 + ks) * 128;
-                            const float2 bh = *reinterpret_cast<const float2*>(wf + lane * 2);
-                            const float2 bl = *reinterpret_cast<const float2*>(wf + 64 + lane * 2);
+                            for (int e = 0; e < 4; ++e) al[e] = tf32_lo(__uint_as_float(ah[e]));
+                            const float2 bh = *reinterpret_cast<const float2*>(Wfrag + (size_t)((il * JW + warp) * 2 + ks) * 64 + lane * 2);
+                            const float2 bl = make_float2(__uint_as_float(tf32_lo(bh.x)), __uint_as_float(tf32_lo(bh.y)));
                             mma_tf32_m16n8k8(cc, al[0], al[1], al[2], al[3], __float_as_uint(bh.x), __float_as_uint(bh.y));
                             mma_tf32_m16n8k8(cc, ah[0], ah[1], ah[2], ah[3], __float_as_uint(bl.x), __float_as_uint(bl.y));
                             mma_tf32_m16n8k8(cc, ah[0], ah[1], ah[2], ah[3], __float_as_uint(bh.x), __float_as_uint(bh.y));
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                 st4(ds, make_float4(duf[0], duf[1], duf[2], duf[3]));
                 st4(ds + 128, make_float4(duf[4], duf[5], duf[6], duf[7]));
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
             // sum the 8 capsules' du fragments; thread <-> (ii, lane, half)
             for (int e = threadIdx.x; e < DUB * 64; e += NT) {
                 const int l = e & 31, half = (e >> 5) & 1, ii = e >> 6;
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
                     *reinterpret_cast<float2*>(dst + (b0 + 8) * 4 + kk) = make_float2(sum.z, sum.w);
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         }
     }
 
@@ -315,30 +329,44 @@ __global__ void __launch_bounds__(32 * kGmJW + 32, 1) k_grad_mma(GradParams p) {
     }
 }
 
-template <int M>
+template <int M, int JW>
 int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
-    const size_t smem = ((size_t)kGmIT * kGmJW * 256 + kGmIT * kGmJW * 128 + kGmJW * 32 * kGmGStride + kGmJW * kGmDub * 256 +
-                         (size_t)gm_stages(M) * (256 + (M - 1) * kGmJW * 32)) * sizeof(float) + 16 * gm_stages(M);
-    auto kern = k_grad_mma<M>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, kGmJW)), block(32 * kGmJW + 32);
+    const size_t smem = ((size_t)gm_fixed_floats(JW) + (size_t)gm_stages(M, JW) * gm_stage_floats(M, JW)) * sizeof(float) +
+                        16 * gm_stages(M, JW);
+    auto kern = k_grad_mma<M, JW>;
+    { static bool attr_set = false;
+      if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; } }
+    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, JW)), block(32 * JW + 32);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();
     return 0;
 }
 
-}  // namespace
-
-// D == 16, K == 8, 8 capsules per CTA (Plan::JW == 8), R <= 5
-int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {
+template <int JW>
+int launch_m(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     switch (pl.M) {
-        case 1: return launch_t<1>(pl, gp, st);
-        case 3: return launch_t<3>(pl, gp, st);
-        case 5: return launch_t<5>(pl, gp, st);
-        case 7: return launch_t<7>(pl, gp, st);
-        case 9: return launch_t<9>(pl, gp, st);
+        case 1: return launch_t<1, JW>(pl, gp, st);
+        case 3: return launch_t<3, JW>(pl, gp, st);
+        case 5: return launch_t<5, JW>(pl, gp, st);
+        case 7: return launch_t<7, JW>(pl, gp, st);
+        case 9: return launch_t<9, JW>(pl, gp, st);
     }
     return fail(CAPS_E_UNSUPPORTED, "R=%d unsupported", pl.R);
+}
+
+}  // namespace
+
+int g_grad_jw = 0;   // tuning knob "gradjw": 0 = auto, 8 or 11
+
+// output capsules per CTA of the mma gradient kernel: 11 when that saves a j-group, else 8
+int grad_mma_jw(const Plan& pl) {
+    if (g_grad_jw == 8 || g_grad_jw == 11) return g_grad_jw;
+    return cdiv(pl.C, 11) < cdiv(pl.C, 8) ? 11 : 8;
+}
+
+// D == 16, K == 8, C >= 7, R <= 5.  Writes cdiv(C, grad_mma_jw(pl)) du partials.
+int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {
+    return grad_mma_jw(pl) == 11 ? launch_m<11>(pl, gp, st) : launch_m<8>(pl, gp, st);
 }
 
 }  // namespace caps
