@@ -31,14 +31,14 @@ constexpr int kGmIT = 8;          // input capsules per CTA
 // Consumer warps (= output capsules) per CTA: 8 or 11.  11 + the producer warp = 384 threads is the most that still
 // leaves 168 registers per thread (X^m alone takes 16 M); three warps per scheduler instead of two hide more of the
 // LDS -> split -> HMMA chain, and C = 43 is 4 x 11 - 1.
-__host__ __device__ constexpr int gm_dub(int JW) { return JW == 8 ? 8 : 4; }          // input capsules per du reduction round
+__host__ __device__ constexpr int gm_dub(int) { return 2; }          // input capsules per du reduction round (double-buffered)
 __host__ __device__ constexpr int gm_stage_floats(int M, int JW) { return 272 + (M - 1) * JW * 32; }
 __host__ __device__ constexpr int gm_fixed_floats(int JW) {
-    return kGmIT * JW * 128 /* Wfrag */ + kGmIT * JW * 128 /* dWsm */ + JW * 32 * 16 /* Gs */ + JW * gm_dub(JW) * 256 /* dusm */;
+    return kGmIT * JW * 128 /* Wfrag */ + kGmIT * JW * 128 /* dWsm */ + JW * 32 * 16 /* Gs */ + 2 * JW * gm_dub(JW) * 256 /* dusm */;
 }
 // operand ring depth (units in flight per CTA): what fits next to the fixed tiles, at most 8
 __host__ __device__ constexpr int gm_stages(int M, int JW) {
-    int ns = (227 * 1024 - 256 - gm_fixed_floats(JW) * 4) / (gm_stage_floats(M, JW) * 4 + 16);
+    int ns = (227 * 1024 - 256 - 64 - gm_fixed_floats(JW) * 4) / (gm_stage_floats(M, JW) * 4 + 16);
     return ns > 8 ? 8 : ns;
 }
 // G tile of a warp: [32 samples][16 dims], no padding, with the 4-float column groups XOR-swizzled by sample bits 1
@@ -92,6 +92,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time: wrong for an event loop)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try(bar, parity))
@@ -117,10 +124,11 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     float* Wfrag = smem;                                   // [IT][JW][ks 2][32 lanes][2]
     float* dWsm = Wfrag + IT * JW * 128;                   // [IT][JW][32 lanes][4]
     float* Gs = dWsm + IT * JW * 128;                      // [JW][32][16] swizzled
-    float* dusm = Gs + JW * 32 * 16;                       // [JW][DUB][half 2][32 lanes][4]
-    float* ring = dusm + JW * DUB * 256;                   // [NS][ u tile [kq 2][32][4], halves kGmUSkew apart | coef rows [M-1][JW][32] ]
+    float* dusm = Gs + JW * 32 * 16;                       // [buf 2][JW][DUB][half 2][32 lanes][4]
+    float* ring = dusm + 2 * JW * DUB * 256;                   // [NS][ u tile [kq 2][32][4], halves kGmUSkew apart | coef rows [M-1][JW][32] ]
     const uint32_t bars = smem_u32(ring + NS * SF);        // full[NS], empty[NS]
     const uint32_t bar_full = bars, bar_empty = bars + 8 * NS;
+    const uint32_t bar_dufull = bars + 16 * NS, bar_dufree = bar_dufull + 16;      // [2] each: du round buffers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
@@ -147,24 +155,30 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     for (int e = threadIdx.x; e < IT * JW * 128; e += blockDim.x) dWsm[e] = 0.f;
     if (threadIdx.x == 0) {
         for (int q = 0; q < NS; ++q) { mbar_init(bar_full + 8 * q, 1); mbar_init(bar_empty + 8 * q, JW); }
+        for (int q = 0; q < 2; ++q) { mbar_init(bar_dufull + 8 * q, JW); mbar_init(bar_dufree + 8 * q, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == JW) {
-        // ===== producer warp: one elected lane streams (tile, il) stages, NS ahead =====
+        // ===== service warp: (1) one elected lane streams (tile, il) stages into the ring, NS ahead;
+        // (2) the whole warp sums the consumer warps' du fragments of each finished round and writes the CTA's
+        // partial -- so the consumers never meet at a CTA barrier.  Event loop over the two non-blocking waits.
         const uint32_t ubytes = 2 * 32 * 4 * 4, cbytes = (uint32_t)njv * 128u;
         int ncoef = 0;
 #pragma unroll
         for (int m = 0; m < M; ++m) ncoef += p.coef[m] != nullptr;
         const uint32_t txbytes = ubytes + (uint32_t)ncoef * cbytes;
-        int q = 0;
+        int q = 0, ftile = 0, fil = 0;                      // next stage to fill
         uint32_t ph = 1;
-        for (int tile = 0; tile < p.nbt; ++tile)
-            for (int il = 0; il < ni; ++il) {
-                mbar_wait(bar_empty + 8 * q, ph);
+        const int rounds = p.nbt * (IT / DUB);
+        int rr = 0;                                         // next round to reduce
+        const int gg = lane >> 2, tt = lane & 3;
+        const int kq = (2 * tt) >> 2, kk = (2 * tt) & 3;
+        while (ftile < p.nbt || rr < rounds) {
+            if (ftile < p.nbt && mbar_test(bar_empty + 8 * q, ph)) {
                 if (lane == 0) {
-                    const size_t ti = (size_t)tile * p.N + i0 + il;
+                    const size_t ti = (size_t)ftile * p.N + i0 + fil;
                     const uint32_t dst = smem_u32(ring + q * SF), bar = bar_full + 8 * q;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(txbytes) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -182,8 +196,37 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                 }
                 __syncwarp();
                 if (++q == NS) { q = 0; ph ^= 1; }
+                if (++fil == ni) { fil = 0; ++ftile; }
+                continue;
             }
-        return;                                             // the consumers synchronise among themselves (named barrier 1)
+            if (rr < rounds && mbar_test(bar_dufull + 8 * (rr & 1), (rr >> 1) & 1)) {
+                const int tile = rr / (IT / DUB), ib = (rr % (IT / DUB)) * DUB;
+                const float* dbuf = dusm + (size_t)(rr & 1) * JW * DUB * 256;
+#pragma unroll
+                for (int e = 0; e < DUB * 2; ++e) {         // lane <-> fragment lane; e = (ii, half)
+                    const int half = e & 1, ii = e >> 1, il = ib + ii;
+                    if (il < ni) {
+                        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int w = 0; w < JW; ++w) {
+                            const float4 x = *reinterpret_cast<const float4*>(dbuf + (size_t)(((w * DUB + ii) * 2 + half) * 32 + lane) * 4);
+                            sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+                        }
+                        // fragment (mt = half): c0 (b = 16mt+gg, k = 2tt), c1 (.., k = 2tt+1), c2 (b + 8, k = 2tt), c3 (b + 8, 2tt+1)
+                        const int b0 = 16 * half + gg;
+                        float* dst = p.du_part + ((((size_t)blockIdx.y * p.nbt + tile) * p.N + i0 + il) * 2 + kq) * kLanes * 4;
+                        *reinterpret_cast<float2*>(dst + b0 * 4 + kk) = make_float2(sum.x, sum.y);
+                        *reinterpret_cast<float2*>(dst + (b0 + 8) * 4 + kk) = make_float2(sum.z, sum.w);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_dufree + 8 * (rr & 1));
+                ++rr;
+                continue;
+            }
+            __nanosleep(32);
+        }
+        return;
     }
 
     float* Gw = Gs + warp * 32 * 16;
@@ -197,6 +240,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     const uint32_t lm_a0 = smem_u32(Gw + lm_row * 16 + (((lane >> 4) * 4) ^ gm_sigma(lm_row)));     // ks = 0
     const uint32_t lm_a1 = smem_u32(Gw + lm_row * 16 + (((lane >> 4) * 4 + 8) ^ gm_sigma(lm_row))); // ks = 1
     int sq = 0;                                             // ring position of the current unit
+    int rnd = 0;                                            // du round counter (buffer = rnd & 1)
     uint32_t sph = 0;
     // X^m of (tile, j): 16 floats per term and lane; term 0 arrives pre-multiplied by its constant coupling 1/C
     // (caps_route_backward has k_dsquash do it), so nothing depends on the loads until the next unit.  The loads
@@ -217,7 +261,10 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     };
     if (jvalid) load_x(0);
     for (int tile = 0; tile < p.nbt; ++tile) {
-        for (int ib = 0; ib < IT; ib += DUB) {
+        for (int ib = 0; ib < IT; ib += DUB, ++rnd) {
+            // this round's du buffer must have been drained by the service warp (two rounds ago)
+            mbar_wait(bar_dufree + 8 * (rnd & 1), ((rnd >> 1) & 1) ^ 1);
+            float* dbuf = dusm + (size_t)(rnd & 1) * JW * DUB * 256;
 #pragma unroll 1
             for (int ii = 0; ii < DUB; ++ii) {
                 const int il = ib + ii;
@@ -286,53 +333,32 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     if (lane == 0) mbar_arrive(bar_empty + 8 * sq);
                     if (++sq == NS) { sq = 0; sph ^= 1; }
                 }
-                float* ds = dusm + (size_t)((warp * DUB + ii) * 2) * 128 + lane * 4;   // [warp][ii][half][lane][4]
+                float* ds = dbuf + (size_t)((warp * DUB + ii) * 2) * 128 + lane * 4;   // [warp][ii][half][lane][4]
                 st4(ds, make_float4(duf[0], duf[1], duf[2], duf[3]));
                 st4(ds + 128, make_float4(duf[4], duf[5], duf[6], duf[7]));
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-            // sum the 8 capsules' du fragments; thread <-> (ii, lane, half)
-            for (int e = threadIdx.x; e < DUB * 64; e += NT) {
-                const int l = e & 31, half = (e >> 5) & 1, ii = e >> 6;
-                const int il = ib + ii;
-                if (il < ni) {
-                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int w = 0; w < JW; ++w) {
-                        const float4 x = *reinterpret_cast<const float4*>(dusm + (size_t)(((w * DUB + ii) * 2 + half) * 32 + l) * 4);
-                        sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
-                    }
-                    // fragment (mt = half): c0 (b = 16mt+gg, k = 2tt), c1 (.., k = 2tt+1), c2 (b + 8, k = 2tt), c3 (b + 8, 2tt+1)
-                    const int gg = l >> 2, tt = l & 3, b0 = 16 * half + gg;
-                    const int kq = (2 * tt) >> 2, kk = (2 * tt) & 3;
-                    float* dst = p.du_part + ((((size_t)blockIdx.y * p.nbt + tile) * p.N + i0 + il) * 2 + kq) * kLanes * 4;
-                    *reinterpret_cast<float2*>(dst + b0 * 4 + kk) = make_float2(sum.x, sum.y);
-                    *reinterpret_cast<float2*>(dst + (b0 + 8) * 4 + kk) = make_float2(sum.z, sum.w);
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_dufull + 8 * (rnd & 1));        // release: this warp's fragments are visible
         }
     }
 
     // dW fragments -> public [N][C][8][16]:  c0 (d = g, k = 2t), c1 (d = g, k = 2t+1), c2 (d = g+8, k = 2t), c3 (d = g+8, k = 2t+1)
-    for (int e = threadIdx.x; e < IT * JW * 32; e += NT) {
-        const int l = e & 31, w = (e >> 5) % JW, il = e / (32 * JW);
-        if (il < ni && w < njv) {
-            const float4 v = *reinterpret_cast<const float4*>(dWsm + (size_t)e * 4);
-            const int gg = l >> 2, tt = l & 3;
-            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j0 + w) * 128;
-            dst[(2 * tt) * 16 + gg] = v.x;
-            dst[(2 * tt + 1) * 16 + gg] = v.y;
-            dst[(2 * tt) * 16 + gg + 8] = v.z;
-            dst[(2 * tt + 1) * 16 + gg + 8] = v.w;
+    // (each warp writes the fragments it accumulated itself: no barrier needed)
+    if (jvalid)
+        for (int il = 0; il < ni; ++il) {
+            const float4 v = *reinterpret_cast<const float4*>(dWsm + (size_t)((il * JW + warp) * 32 + lane) * 4);
+            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j) * 128;
+            dst[(2 * t) * 16 + g] = v.x;
+            dst[(2 * t + 1) * 16 + g] = v.y;
+            dst[(2 * t) * 16 + g + 8] = v.z;
+            dst[(2 * t + 1) * 16 + g + 8] = v.w;
         }
-    }
 }
 
 template <int M, int JW>
 int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     const size_t smem = ((size_t)gm_fixed_floats(JW) + (size_t)gm_stages(M, JW) * gm_stage_floats(M, JW)) * sizeof(float) +
-                        16 * gm_stages(M, JW);
+                        16 * gm_stages(M, JW) + 32;
     auto kern = k_grad_mma<M, JW>;
     { static bool attr_set = false;
       if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; } }
@@ -358,11 +384,10 @@ int launch_m(const Plan& pl, const GradParams& gp, cudaStream_t st) {
 
 int g_grad_jw = 0;   // tuning knob "gradjw": 0 = auto, 8 or 11
 
-// output capsules per CTA of the mma gradient kernel: 11 when that saves a j-group, else 8
-int grad_mma_jw(const Plan& pl) {
-    if (g_grad_jw == 8 || g_grad_jw == 11) return g_grad_jw;
-    return cdiv(pl.C, 11) < cdiv(pl.C, 8) ? 11 : 8;
-}
+// output capsules per CTA of the mma gradient kernel.  11 never needs more j-groups than 8, and with 12 warps the
+// service warp shares a scheduler with two consumers instead of three (JW = 8 measured 11.1 ms against 7.8 ms at
+// C = 43); 8 stays selectable for experiments and as a second summation grouping in the tests.
+int grad_mma_jw(const Plan&) { return g_grad_jw == 8 ? 8 : 11; }
 
 // D == 16, K == 8, C >= 7, R <= 5.  Writes cdiv(C, grad_mma_jw(pl)) du partials.
 int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {

@@ -169,6 +169,15 @@ def test_tensor_core_and_fma_engines_agree(capsb):
         capsb._cabi.set_tuning('gradmma', 1)
     for k in ('v', 'c', 'du', 'dW'):
         assert rel_err(res['tensor'][k], res['fma'][k]) < 5e-6, k
+    # 8 instead of 11 capsules per CTA in the gradient kernel: dW is bit-identical (the batch sum of one (i, j)
+    # never crosses warps), du only regroups the sum over j
+    try:
+        capsb._cabi.set_tuning('gradjw', 8)
+        alt = cuda_step(capsb, u, W, y, R)
+    finally:
+        capsb._cabi.set_tuning('gradjw', 0)
+    assert np.array_equal(alt['dW'], res['tensor']['dW'])
+    assert rel_err(alt['du'], res['tensor']['du']) < 5e-6
 
 
 def test_batch_permutation_and_additivity_at_full_size(capsb):
