@@ -1,0 +1,347 @@
+// probe_overlap.cu -- what slows the tcgen05 pass kernel's L / A modes down to ~2x the MMA-bound time?
+// One CTA per SM, 384 threads like k_pass_tc: warp 11 issues "stages" of three dependent kind::tf32 MMAs
+// (M = 128, N = 128, K = 8) into four rotating TMEM accumulators, one commit per stage; warps 0..7 play the
+// epilogue in one of several modes.  Prints issuer cycles per stage for every mode.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/probe_overlap tools/probe_overlap.cu
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ int g_poll;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int poll = 0) {
+    long spins = 0;
+    if (poll) { while (!mbar_test(bar, parity)) if (++spins > (1L << 24)) { printf("mbar_wait timeout\n"); __trap(); } return; }
+    while (!mbar_try(bar, parity))
+        if (++spins > (1L << 22)) { printf("mbar_wait timeout\n"); __trap(); }
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void stage_mma(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                          uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe, pt, pf;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "setp.eq.b32 pt, 0, 0;\n\t"
+        "setp.ne.b32 pf, 0, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, pf;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(bar)
+        : "memory");
+}
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[64]);
+template <>
+__device__ __forceinline__ void tmem_ld<64>(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+enum { kFree = 0, kHandshake, kHandLd, kHandLdFma, kFreeFma, kFreeLd, kFreeTest, kFreeTry, kHandLdFmaDeep, kFree64, kModes };
+static const char* kNames[kModes] = {
+    "issuer free-running, epilogue warps exit",
+    "handshake only (wait full, arrive empty)",
+    "handshake + LDTM.x64",
+    "handshake + LDTM.x64 + 64 FFMA",
+    "free-running issuer, epilogue warps spin FFMA",
+    "free-running issuer, epilogue warps spin LDTM.x64",
+    "free-running issuer, epilogue warps poll test_wait",
+    "free-running issuer, epilogue warps poll try_wait",
+    "handshake + LDTM.x64 + 64 FFMA, N = 64, 8 accumulators, warps take alternate stages",
+    "issuer free-running, N = 64",
+};
+
+__global__ void __launch_bounds__(384, 1) k_overlap(int mode, int reps, long long* cycles, float* sink, int nacc_arg = 0, int poll = 0, int epi_warps = 8) {
+    __shared__ __align__(1024) float sA[2][2 * 128 * 4];
+    __shared__ __align__(1024) float sB[2][2 * 128 * 4];
+    __shared__ __align__(8) uint64_t bars[24];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < 2 * 2 * 128 * 4; e += 384) { (&sA[0][0])[e] = 1.0f + (e & 7) * 0.125f; (&sB[0][0])[e] = 0.5f + (e & 3) * 0.25f; }
+    const bool deep = mode == kHandLdFmaDeep;
+    const int nacc = (nacc_arg && nacc_arg != 99) ? nacc_arg : (deep ? 8 : 4), ncol = (deep || mode == kFree64) ? 64 : 128;
+    const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[8]), never = smem_u32(&bars[16]);
+    if (tid == 0) {
+        for (int t = 0; t < 8; ++t) { mbar_init(full + 8 * t, 1); mbar_init(empty + 8 * t, deep ? 4 : epi_warps); }
+        mbar_init(never, 1);
+        mbar_init(smem_u32(&bars[20]), 1);
+        mbar_arrive(smem_u32(&bars[20]));      // 'done': phase 0 already complete
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const bool hand = mode == kHandshake || mode == kHandLd || mode == kHandLdFma || deep;
+    if (warp == 11) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ncol >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t a_hi = make_desc(smem_u32(sA[0]), 2048, 128), a_lo = make_desc(smem_u32(sA[1]), 2048, 128);
+        const uint64_t b_hi = make_desc(smem_u32(sB[0]), 2048, 128), b_lo = make_desc(smem_u32(sB[1]), 2048, 128);
+        const long long t0 = clock64();
+        for (int n = 0; n < reps; ++n) {
+            const int t = n % nacc;
+            if (hand) mbar_wait(empty + 8 * t, ((n / nacc) & 1) ^ 1, poll);
+            if (mode == kFree && nacc_arg == 99) mbar_wait(smem_u32(&bars[20]), 0, poll);   // issuer chain alone: a wait that always passes
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            stage_mma(tmem_base + t * ncol, a_hi, a_lo, b_hi, b_lo, idesc, full + 8 * t);
+        }
+        // the last stage's commit
+        const int n = reps - 1;
+        if (!hand) mbar_wait(full + 8 * (n % nacc), ((n / nacc) & 1));
+        if (hand) for (int t = 0; t < nacc; ++t) {          // all epilogues done
+            const int last = ((reps - 1 - t) / nacc) * nacc + t;
+            if (last >= 0) mbar_wait(empty + 8 * t, (last / nacc) & 1);
+        }
+        if (lane == 0) cycles[blockIdx.x] = clock64() - t0;
+        if (!hand && lane == 0) mbar_arrive(never);            // release the spinners
+    } else if (warp < epi_warps) {
+        const int q = warp & 3, jh = warp >> 2;
+        float acc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc[e] = 0.001f * e;
+        uint32_t uh[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) uh[e] = __float_as_uint(1.f + e);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (deep ? 0 : jh * 64);
+        if (hand) {
+            for (int n = deep ? jh : 0; n < reps; n += deep ? 2 : 1) {
+                const int t = n % nacc;
+                mbar_wait(full + 8 * t, (n / nacc) & 1, poll);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (mode != kHandshake) tmem_ld<64>(lane_base + t * ncol, uh);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + 8 * t);
+                if (mode == kHandLdFma || deep) {
+#pragma unroll
+                    for (int e = 0; e < 64; ++e) acc[e] = fmaf(__uint_as_float(uh[e]), 1.0001f, acc[e]);
+                }
+            }
+        } else if (mode == kFreeFma) {
+            while (!mbar_test(never, 0)) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int e = 0; e < 64; ++e) acc[e] = fmaf(acc[e], 1.0001f, 0.5f);
+            }
+        } else if (mode == kFreeLd) {
+            while (!mbar_test(never, 0)) {
+                tmem_ld<64>(lane_base, uh);
+#pragma unroll
+                for (int e = 0; e < 64; e += 16) acc[e] += __uint_as_float(uh[e]);
+            }
+        } else if (mode == kFreeTest) {
+            while (!mbar_test(never, 0)) {}
+        } else if (mode == kFreeTry) {
+            while (!mbar_try(never, 0)) {}
+        }
+        float x = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) x += acc[e];
+        if (x == 1.2345f) sink[tid] = x;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+// ---- second probe: the full epilogue load with NISS issuer warps (11, 10, ...), optional look-ahead probing of the
+// next barrier in the issuer, optional FFMA2 epilogue.  Cycles per stage measured by epilogue warp 0.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    uint64_t a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
+}
+template <int NISS, int LOOK, int FMA2, int EPIFMA, int EPIV = 0>
+__global__ void __launch_bounds__(384, 1) k_pipe(int reps, long long* cycles, float* sink) {
+    __shared__ __align__(1024) float sA[2][2 * 128 * 4];
+    __shared__ __align__(1024) float sB[2][2 * 128 * 4];
+    __shared__ __align__(8) uint64_t bars[8];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < 2 * 2 * 128 * 4; e += 384) { (&sA[0][0])[e] = 1.0f + (e & 7) * 0.125f; (&sB[0][0])[e] = 0.5f + (e & 3) * 0.25f; }
+    const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[4]);
+    if (tid == 0)
+        for (int t = 0; t < 4; ++t) { mbar_init(full + 8 * t, 1); mbar_init(empty + 8 * t, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp >= 12 - NISS) {
+        const int k = warp - (12 - NISS);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t a_hi = make_desc(smem_u32(sA[0]), 2048, 128), a_lo = make_desc(smem_u32(sA[1]), 2048, 128);
+        const uint64_t b_hi = make_desc(smem_u32(sB[0]), 2048, 128), b_lo = make_desc(smem_u32(sB[1]), 2048, 128);
+        bool ok = false;
+        for (int n = k; n < reps; n += NISS) {
+            const int t = n & 3;
+            if (!ok) { long spins = 0; while (!mbar_try(empty + 8 * t, ((n >> 2) & 1) ^ 1)) if (++spins > (1L << 22)) __trap(); }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            stage_mma(tmem_base + t * 128, a_hi, a_lo, b_hi, b_lo, idesc, full + 8 * t);
+            ok = false;
+            if (LOOK && n + NISS < reps) ok = mbar_test(empty + 8 * ((n + NISS) & 3), (((n + NISS) >> 2) & 1) ^ 1);
+        }
+    } else if (warp < 8) {
+        const int q = warp & 3, jh = warp >> 2;
+        float acc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc[e] = 0.001f * e;
+        uint32_t uh[64];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + jh * 64;
+        const long long t0 = clock64();
+        bool rdy = false;
+        for (int n = 0; n < reps; ++n) {
+            const int t = n & 3;
+            if (!rdy) { long spins = 0; while (!mbar_try(full + 8 * t, (n >> 2) & 1)) if (++spins > (1L << 22)) __trap(); }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tmem_ld<64>(lane_base + t * 128, uh);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (!(EPIV & 2)) __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * t);
+            rdy = false;
+            if ((EPIV & 1) && n + 1 < reps) rdy = mbar_test(full + 8 * ((n + 1) & 3), ((n + 1) >> 2) & 1);
+            if (EPIFMA) {
+                if (FMA2) {
+#pragma unroll
+                    for (int e = 0; e < 64; e += 2) ffma2(acc[e], acc[e + 1], 1.0001f, 1.0001f, __uint_as_float(uh[e]), __uint_as_float(uh[e + 1]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 64; ++e) acc[e] = fmaf(__uint_as_float(uh[e]), 1.0001f, acc[e]);
+                }
+            }
+        }
+        if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+        float x = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) x += acc[e];
+        if (x == 1.2345f) sink[tid] = x;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+template <int NISS, int LOOK, int FMA2, int EPIFMA, int EPIV = 0>
+void run_pipe(int reps, long long* dc, float* sink) {
+    k_pipe<NISS, LOOK, FMA2, EPIFMA, EPIV><<<148, 384>>>(reps, dc, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("k_pipe: CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+    long long hc[148];
+    cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (int i = 0; i < 148; ++i) s += (double)hc[i];
+    printf("issuers %d lookahead %d ffma2 %d epilogue-fma %d epi-variant %d: %7.1f cycles per stage\n", NISS, LOOK, FMA2, EPIFMA, EPIV, s / 148 / reps);
+}
+
+int main() {
+    long long* dc;
+    float* sink;
+    cudaMalloc(&dc, 148 * sizeof(long long));
+    cudaMalloc(&sink, 4096);
+    const int reps = 4000;
+    for (int ctas : {1, 148})
+        for (int mode = 0; mode < kModes; ++mode) {
+            k_overlap<<<ctas, 384>>>(mode, reps, dc, sink);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 1; }
+            long long hc[148];
+            cudaMemcpy(hc, dc, ctas * sizeof(long long), cudaMemcpyDeviceToHost);
+            double s = 0;
+            for (int i = 0; i < ctas; ++i) s += (double)hc[i];
+            printf("%3d CTAs  mode %d: %7.1f cycles per stage   (%s)\n", ctas, mode, s / ctas / reps, kNames[mode]);
+        }
+    printf("---- full epilogue load, issuer variants (148 CTAs)\n");
+    run_pipe<1, 0, 0, 0>(reps, dc, sink);
+    run_pipe<1, 1, 0, 0>(reps, dc, sink);
+    run_pipe<2, 0, 0, 0>(reps, dc, sink);
+    run_pipe<2, 1, 0, 0>(reps, dc, sink);
+    run_pipe<4, 1, 0, 0>(reps, dc, sink);
+    run_pipe<1, 0, 0, 1>(reps, dc, sink);
+    run_pipe<1, 1, 0, 1>(reps, dc, sink);
+    run_pipe<2, 0, 0, 1>(reps, dc, sink);
+    run_pipe<2, 1, 0, 1>(reps, dc, sink);
+    run_pipe<3, 1, 0, 1>(reps, dc, sink);
+    run_pipe<4, 0, 0, 1>(reps, dc, sink);
+    run_pipe<4, 1, 0, 1>(reps, dc, sink);
+    run_pipe<2, 1, 1, 1>(reps, dc, sink);
+    run_pipe<4, 1, 1, 1>(reps, dc, sink);
+    run_pipe<2, 0, 0, 1, 1>(reps, dc, sink);
+    run_pipe<2, 0, 0, 1, 2>(reps, dc, sink);
+    run_pipe<2, 0, 0, 1, 3>(reps, dc, sink);
+    run_pipe<2, 0, 1, 1, 3>(reps, dc, sink);
+    run_pipe<2, 0, 0, 0, 3>(reps, dc, sink);
+    printf("---- handshake-only loop latency vs ring depth / wait flavour (1 CTA)\n");
+    for (int poll = 0; poll < 2; ++poll)
+        for (int nacc : {1, 2, 4})
+            for (int mode : {(int)kHandshake, (int)kHandLdFma}) {
+                k_overlap<<<1, 384>>>(mode, reps, dc, sink, nacc, poll, 8);
+                cudaDeviceSynchronize();
+                long long hc;
+                cudaMemcpy(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+                printf("poll=%d nacc=%d mode %d: %7.1f cycles per stage\n", poll, nacc, mode, (double)hc / reps);
+            }
+    for (int poll = 0; poll < 2; ++poll) {
+        k_overlap<<<1, 384>>>(kFree, reps, dc, sink, 99, poll, 8);
+        cudaDeviceSynchronize();
+        long long hc;
+        cudaMemcpy(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+        printf("poll=%d issuer with an always-passing wait per stage, no epilogue: %7.1f cycles per stage\n", poll, (double)hc / reps);
+    }
+    printf("---- handshake-only with 4 epilogue warps (one per quadrant)\n");
+    for (int poll = 0; poll < 2; ++poll) {
+        k_overlap<<<1, 384>>>(kHandshake, reps, dc, sink, 4, poll, 4);
+        cudaDeviceSynchronize();
+        long long hc;
+        cudaMemcpy(&hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+        printf("poll=%d nacc=4 epi_warps=4: %7.1f cycles per stage\n", poll, (double)hc / reps);
+    }
+    return 0;
+}
