@@ -401,21 +401,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
             }
         } else
         for (int n = 0; n < n_i; ++n) {
+            // Every epilogue warp handles every stage, so the stage rate is bounded by this loop's serial chain of fixed
+            // latencies (tools/probe_overlap.cu: a try_wait round trip is ~75 cycles even on a completed mbarrier, LDS
+            // ~70, LDTM ~45; two warps per scheduler run their FMA bursts in phase).  Hence: ONE wait per stage --
+            // tmem_full(n) is signalled by a commit behind MMAs whose issuer had already observed smem_full(n), so stage
+            // n's bulk copies (the kModeA coefficients) have landed by then -- and the coefficient LDS rides under the LDTM.
             const int t = n & (kTcAccum - 1);
             const int i = i_begin + n;
             float cc[JPW];
 #pragma unroll
             for (int jj = 0; jj < JPW; ++jj) cc[jj] = 0.f;
-            if (MODE == kModeA) {
-                mbar_wait(smem_full + 8 * s, sph);               // the bulk copies of stage s have landed
-                if (tvalid) {
-                    const uint32_t ca = stages + (uint32_t)s * kTcStageBytes + coef_off;
-#pragma unroll
-                    for (int jj = 0; jj < JPW; ++jj)
-                        if (j0 + jj < p.C) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cc[jj]) : "r"(ca + jj * 128) : "memory");
-                }
-            }
             mbar_wait(tmem_full + 8 * t, (n >> kTcAccumLog2) & 1);
+            if (MODE == kModeA && tvalid) {
+                const uint32_t ca = stages + (uint32_t)s * kTcStageBytes + coef_off;
+#pragma unroll
+                for (int jj = 0; jj < JPW; ++jj)
+                    if (j0 + jj < p.C) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cc[jj]) : "r"(ca + jj * 128) : "memory");
+            }
             tc_fence_after();
             float uh[NC];
             tmem_ld<NC>(lane_base + (uint32_t)(t * kTcN), uh);

@@ -195,6 +195,18 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
 }
+__device__ __forceinline__ uint32_t fused_fma_wait(uint64_t (&A)[32], const uint64_t (&U)[32], uint64_t cc2, uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%66], %67;\n\t"
+        "fma.rn.f32x2 %0, %33, %65, %0;\n\tfma.rn.f32x2 %1, %34, %65, %1;\n\tfma.rn.f32x2 %2, %35, %65, %2;\n\tfma.rn.f32x2 %3, %36, %65, %3;\n\tfma.rn.f32x2 %4, %37, %65, %4;\n\tfma.rn.f32x2 %5, %38, %65, %5;\n\tfma.rn.f32x2 %6, %39, %65, %6;\n\tfma.rn.f32x2 %7, %40, %65, %7;\n\tfma.rn.f32x2 %8, %41, %65, %8;\n\tfma.rn.f32x2 %9, %42, %65, %9;\n\tfma.rn.f32x2 %10, %43, %65, %10;\n\tfma.rn.f32x2 %11, %44, %65, %11;\n\tfma.rn.f32x2 %12, %45, %65, %12;\n\tfma.rn.f32x2 %13, %46, %65, %13;\n\tfma.rn.f32x2 %14, %47, %65, %14;\n\tfma.rn.f32x2 %15, %48, %65, %15;\n\tfma.rn.f32x2 %16, %49, %65, %16;\n\tfma.rn.f32x2 %17, %50, %65, %17;\n\tfma.rn.f32x2 %18, %51, %65, %18;\n\tfma.rn.f32x2 %19, %52, %65, %19;\n\tfma.rn.f32x2 %20, %53, %65, %20;\n\tfma.rn.f32x2 %21, %54, %65, %21;\n\tfma.rn.f32x2 %22, %55, %65, %22;\n\tfma.rn.f32x2 %23, %56, %65, %23;\n\tfma.rn.f32x2 %24, %57, %65, %24;\n\tfma.rn.f32x2 %25, %58, %65, %25;\n\tfma.rn.f32x2 %26, %59, %65, %26;\n\tfma.rn.f32x2 %27, %60, %65, %27;\n\tfma.rn.f32x2 %28, %61, %65, %28;\n\tfma.rn.f32x2 %29, %62, %65, %29;\n\tfma.rn.f32x2 %30, %63, %65, %30;\n\tfma.rn.f32x2 %31, %64, %65, %31;\n\t"
+        "selp.u32 %32, 1, 0, p;\n\t}"
+        : "+l"(A[0]), "+l"(A[1]), "+l"(A[2]), "+l"(A[3]), "+l"(A[4]), "+l"(A[5]), "+l"(A[6]), "+l"(A[7]), "+l"(A[8]), "+l"(A[9]), "+l"(A[10]), "+l"(A[11]), "+l"(A[12]), "+l"(A[13]), "+l"(A[14]), "+l"(A[15]), "+l"(A[16]), "+l"(A[17]), "+l"(A[18]), "+l"(A[19]), "+l"(A[20]), "+l"(A[21]), "+l"(A[22]), "+l"(A[23]), "+l"(A[24]), "+l"(A[25]), "+l"(A[26]), "+l"(A[27]), "+l"(A[28]), "+l"(A[29]), "+l"(A[30]), "+l"(A[31]), "=r"(ok)
+        : "l"(U[0]), "l"(U[1]), "l"(U[2]), "l"(U[3]), "l"(U[4]), "l"(U[5]), "l"(U[6]), "l"(U[7]), "l"(U[8]), "l"(U[9]), "l"(U[10]), "l"(U[11]), "l"(U[12]), "l"(U[13]), "l"(U[14]), "l"(U[15]), "l"(U[16]), "l"(U[17]), "l"(U[18]), "l"(U[19]), "l"(U[20]), "l"(U[21]), "l"(U[22]), "l"(U[23]), "l"(U[24]), "l"(U[25]), "l"(U[26]), "l"(U[27]), "l"(U[28]), "l"(U[29]), "l"(U[30]), "l"(U[31]), "l"(cc2), "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 template <int NISS, int LOOK, int FMA2, int EPIFMA, int EPIV = 0>
 __global__ void __launch_bounds__(384, 1) k_pipe(int reps, long long* cycles, float* sink) {
     __shared__ __align__(1024) float sA[2][2 * 128 * 4];
@@ -249,7 +261,20 @@ __global__ void __launch_bounds__(384, 1) k_pipe(int reps, long long* cycles, fl
             if (lane == 0) mbar_arrive(empty + 8 * t);
             rdy = false;
             if ((EPIV & 1) && n + 1 < reps) rdy = mbar_test(full + 8 * ((n + 1) & 3), ((n + 1) >> 2) & 1);
-            if (EPIFMA) {
+            if (EPIFMA && (EPIV & 4)) {
+                uint64_t A2[32], U2[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(A2[e]) : "f"(acc[2 * e]), "f"(acc[2 * e + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(U2[e]) : "r"(uh[2 * e]), "r"(uh[2 * e + 1]));
+                }
+                uint64_t cc2;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(cc2) : "f"(1.0001f), "f"(1.0001f));
+                const int n1 = n + 1 < reps ? n + 1 : n;
+                rdy = fused_fma_wait(A2, U2, cc2, full + 8 * (n1 & 3), (n1 >> 2) & 1) != 0 && n + 1 < reps;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * e]), "=f"(acc[2 * e + 1]) : "l"(A2[e]));
+            } else if (EPIFMA) {
                 if (FMA2) {
 #pragma unroll
                     for (int e = 0; e < 64; e += 2) ffma2(acc[e], acc[e + 1], 1.0001f, 1.0001f, __uint_as_float(uh[e]), __uint_as_float(uh[e + 1]));
@@ -318,6 +343,8 @@ int main() {
     run_pipe<2, 0, 0, 1, 3>(reps, dc, sink);
     run_pipe<2, 0, 1, 1, 3>(reps, dc, sink);
     run_pipe<2, 0, 0, 0, 3>(reps, dc, sink);
+    run_pipe<2, 0, 1, 1, 4>(reps, dc, sink);
+    run_pipe<2, 0, 1, 1, 6>(reps, dc, sink);
     printf("---- handshake-only loop latency vs ring depth / wait flavour (1 CTA)\n");
     for (int poll = 0; poll < 2; ++poll)
         for (int nacc : {1, 2, 4})
