@@ -306,6 +306,154 @@ void run_pipe(int reps, long long* dc, float* sink) {
     printf("issuers %d lookahead %d ffma2 %d epilogue-fma %d epi-variant %d: %7.1f cycles per stage\n", NISS, LOOK, FMA2, EPIFMA, EPIV, s / 148 / reps);
 }
 
+// ---- third probe: k_pipe plus what the real kernel has around it: a bulk-copy producer ring (NS stages of 16 KB +
+// optional 4 KB of coefficients), the issuer waiting on smem_full, and epilogue extras (coefficient LDS + smem_empty
+// arrive = mode A; 4 coalesced global stores = mode L).
+template <int NISS, int NPROD, int EXTRA, int PAIR = 0>   // PAIR: epilogue waits for two stages at once; EXTRA: 0 none, 1 = A-like (LDS coef + second arrive), 2 = L-like (4 STG per stage)
+__global__ void __launch_bounds__(384, 1) k_full(int reps, long long* cycles, float* sink, const float* src, float* outbuf) {
+    extern __shared__ __align__(1024) uint8_t dsm[];
+    constexpr int NS = 10, SB = (EXTRA == 1) ? 20480 : 16384;
+    __shared__ __align__(8) uint64_t bars[8 + 2 * NS];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t stages = smem_u32(dsm);
+    const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[4]), sfull = smem_u32(&bars[8]), sempty = smem_u32(&bars[8 + NS]);
+    if (tid == 0) {
+        for (int t = 0; t < 4; ++t) { mbar_init(full + 8 * t, 1); mbar_init(empty + 8 * t, 8); }
+        for (int q = 0; q < NS; ++q) { mbar_init(sfull + 8 * q, 1); mbar_init(sempty + 8 * q, EXTRA == 1 ? 9 : 1); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp >= 8 && warp < 8 + NPROD) {
+        const int k = warp - 8;
+        const float* g = src + (size_t)blockIdx.x * 8192;            // each CTA streams its own 32 KB window (L2 resident)
+        for (int n = k; n < reps; n += NPROD) {
+            const int q = n % NS;
+            { long spins = 0; while (!mbar_try(sempty + 8 * q, ((n / NS) & 1) ^ 1)) if (++spins > (1L << 22)) __trap(); }
+            asm volatile(
+                "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+                "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], 8192, [%0];\n\t"
+                "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%4], [%5], 8192, [%0];\n\t}"
+                ::"r"(sfull + 8 * q), "r"(16384), "r"(stages + q * SB), "l"(g + (n & 1) * 4096), "r"(stages + q * SB + 8192), "l"(g + 2048 + (n & 1) * 4096)
+                : "memory");
+        }
+    } else if (warp >= 12 - NISS) {
+        const int k = warp - (12 - NISS);
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t d0 = make_desc(stages, 2048, 128);
+        for (int n = k; n < reps; n += NISS) {
+            const int t = n & 3, q = n % NS;
+            { long spins = 0; while (!mbar_try(empty + 8 * t, ((n >> 2) & 1) ^ 1)) if (++spins > (1L << 22)) __trap(); }
+            { long spins = 0; while (!mbar_try(sfull + 8 * q, (n / NS) & 1)) if (++spins > (1L << 22)) __trap(); }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t a_hi = d0 + (uint64_t)((q * SB) >> 4), a_lo = a_hi + (4096 >> 4), b_hi = a_hi + (8192 >> 4), b_lo = b_hi + (4096 >> 4);
+            stage_mma(tmem_base + t * 128, a_hi, a_lo, b_hi, b_lo, idesc, full + 8 * t);
+            asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+                         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(sempty + 8 * q) : "memory");
+        }
+    } else if (warp < 8) {
+        const int q4 = warp & 3, jh = warp >> 2;
+        float acc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc[e] = src[e * 32 + lane] + 0.001f * e;      // runtime values: stay in registers
+        uint32_t uh[64];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16) + jh * 64;
+        const long long t0 = clock64();
+        for (int n = 0; n < reps; ++n) {
+            const int t = n & 3, q = n % NS;
+            if (PAIR && !(n & 1) && n + 1 < reps) {
+                // both stages' barriers probed in one go: the second round trip hides under the first
+                uint32_t ok0, ok1;
+                asm volatile("{\n\t.reg .pred p0, p1;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p0, [%2], %3;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p1, [%4], %5;\n\t"
+                             "selp.u32 %0, 1, 0, p0;\n\tselp.u32 %1, 1, 0, p1;\n\t}"
+                             : "=r"(ok0), "=r"(ok1)
+                             : "r"(full + 8 * t), "r"((n >> 2) & 1), "r"(full + 8 * ((n + 1) & 3)), "r"(((n + 1) >> 2) & 1) : "memory");
+                if (!ok0) { long spins = 0; while (!mbar_try(full + 8 * t, (n >> 2) & 1)) if (++spins > (1L << 22)) __trap(); }
+                if (!ok1) { long spins = 0; while (!mbar_try(full + 8 * ((n + 1) & 3), ((n + 1) >> 2) & 1)) if (++spins > (1L << 22)) __trap(); }
+            } else if (!PAIR || n + 1 >= reps) {
+                long spins = 0; while (!mbar_try(full + 8 * t, (n >> 2) & 1)) if (++spins > (1L << 22)) __trap();
+            }
+            float cc[4] = {1.0001f, 1.0001f, 1.0001f, 1.0001f};
+            if (EXTRA == 1) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cc[jj]) : "r"(stages + q * SB + 16384 + ((q4 * 8 + jh * 4 + jj) * 32 + lane) * 4) : "memory");
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tmem_ld<64>(lane_base + t * 128, uh);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + 8 * t);
+            if (EXTRA >= 2) {
+                float dots[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 16; d += 4) {
+                        ffma2(d0, d1, __uint_as_float(uh[jj * 16 + d]), __uint_as_float(uh[jj * 16 + d + 1]), acc[jj * 16 + d], acc[jj * 16 + d + 1]);
+                        ffma2(d2, d3, __uint_as_float(uh[jj * 16 + d + 2]), __uint_as_float(uh[jj * 16 + d + 3]), acc[jj * 16 + d + 2], acc[jj * 16 + d + 3]);
+                    }
+                    dots[jj] = (d0 + d1) + (d2 + d3);
+                    if (EXTRA == 2) outbuf[(((size_t)blockIdx.x * 64 + (n & 63)) * 8 + warp) * 128 + jj * 32 + lane] = dots[jj];
+                }
+                if (EXTRA == 3) { acc[0] += dots[0]; acc[17] += dots[1]; acc[34] += dots[2]; acc[51] += dots[3]; }
+                if (EXTRA == 4)
+                    *reinterpret_cast<float4*>(outbuf + (((size_t)blockIdx.x * 64 + (n & 63)) * 8 + warp) * 128 + lane * 4) =
+                        make_float4(dots[0], dots[1], dots[2], dots[3]);
+                if (EXTRA == 5) {        // stores of stage n-1's dots, issued before this stage's FMAs would be better; here: after
+                    float* o = outbuf + (((size_t)blockIdx.x * 64 + (n & 63)) * 8 + warp) * 128 + lane;
+                    asm volatile("st.global.f32 [%0], %1;" ::"l"(o), "f"(dots[0]) : "memory");
+                    asm volatile("st.global.f32 [%0+128], %1;" ::"l"(o), "f"(dots[1]) : "memory");
+                    asm volatile("st.global.f32 [%0+256], %1;" ::"l"(o), "f"(dots[2]) : "memory");
+                    asm volatile("st.global.f32 [%0+384], %1;" ::"l"(o), "f"(dots[3]) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int d = 0; d < 16; d += 2)
+                        ffma2(acc[jj * 16 + d], acc[jj * 16 + d + 1], cc[jj], cc[jj], __uint_as_float(uh[jj * 16 + d]), __uint_as_float(uh[jj * 16 + d + 1]));
+            }
+            if (EXTRA == 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sempty + 8 * q);
+            }
+        }
+        if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+        float x = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) x += acc[e];
+        if (x == 1.2345f) sink[tid] = x;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+template <int NISS, int NPROD, int EXTRA, int PAIR = 0>
+void run_full(int reps, long long* dc, float* sink, const float* src, float* outbuf) {
+    const int smem = 10 * 20480 + 1024;
+    cudaFuncSetAttribute(k_full<NISS, NPROD, EXTRA, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_full<NISS, NPROD, EXTRA, PAIR><<<148, 384, smem>>>(reps, dc, sink, src, outbuf);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("k_full: CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+    long long hc[148];
+    cudaMemcpy(hc, dc, sizeof(hc), cudaMemcpyDeviceToHost);
+    double s = 0;
+    for (int i = 0; i < 148; ++i) s += (double)hc[i];
+    printf("producer ring: issuers %d producers %d extra %d pair %d: %7.1f cycles per stage\n", NISS, NPROD, EXTRA, PAIR, s / 148 / reps);
+}
+
 int main() {
     long long* dc;
     float* sink;
@@ -345,6 +493,24 @@ int main() {
     run_pipe<2, 0, 0, 0, 3>(reps, dc, sink);
     run_pipe<2, 0, 1, 1, 4>(reps, dc, sink);
     run_pipe<2, 0, 1, 1, 6>(reps, dc, sink);
+    {
+        float *src, *outbuf;
+        cudaMalloc(&src, 148 * 8192 * sizeof(float));
+        cudaMemset(src, 0, 148 * 8192 * sizeof(float));
+        cudaMalloc(&outbuf, (size_t)148 * 64 * 8 * 128 * sizeof(float));
+        printf("---- with the producer ring (148 CTAs)\n");
+        run_full<1, 1, 0>(reps, dc, sink, src, outbuf);
+        run_full<2, 1, 0>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 0>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 1>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 2>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 0, 1>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 1, 1>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 2, 1>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 3>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 4>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 5>(reps, dc, sink, src, outbuf);
+    }
     printf("---- handshake-only loop latency vs ring depth / wait flavour (1 CTA)\n");
     for (int poll = 0; poll < 2; ++poll)
         for (int nacc : {1, 2, 4})
