@@ -28,6 +28,7 @@ int g_tune_spt = 0;      // 0 = auto
 int g_tune_isplit = 0;   // 0 = auto
 int g_tune_gradmma = 1;  // 1 = mma.sync gradient kernel where it applies (D == 16, C >= 7)
 int g_tune_hostmb = 0;   // caps_route_step_host: 0 = auto (3 micro-batches from B >= 2048), 1 = single batch
+int g_tune_sbstaged = 1;  // softmax backward through the staged kernel (16 < C <= 48)
 int g_tune_tc = 1;       // 1 = use the tcgen05 pass kernel where it applies, 0 = FFMA kernel only
 
 // ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
@@ -224,6 +225,7 @@ int caps_set_tuning(const char* name, int value) {
         g_grad_jw = value;
         return 0;
     }
+    if (!strcmp(name, "sbstaged")) { g_tune_sbstaged = value != 0; return 0; }
     if (!strcmp(name, "hostmb")) { g_tune_hostmb = value; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
@@ -361,7 +363,16 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
             // the register-resident variant (114 registers) loses to the three-pass one here: the second and
             // third passes hit L1, and occupancy matters more than the re-reads (measured 1.9 vs 1.0 ms)
             if (C <= 16) k_softmax_bwd_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
-            else k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+            else if (C <= 48 && g_tune_sbstaged) {
+                const size_t smem = (size_t)4 * 2 * C * 32 * sizeof(float);
+                static size_t attr_set = 0;
+                if (smem > attr_set) {
+                    CUDA_TRY(cudaFuncSetAttribute(k_softmax_bwd_staged<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_set = smem;
+                }
+                const long nblocks = (long)pl.nbt * N;
+                k_softmax_bwd_staged<48><<<cdiv(nblocks, 4), 128, smem, st>>>(c_r, tmp, beta_next, beta_r, C, nblocks);
+            } else k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
         }
         LAUNCH_CHECK();
         pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
