@@ -70,13 +70,32 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
 }
-// c += a * b with a (4 regs) and b (2 regs) given in fp32; 3xTF32
-__device__ __forceinline__ void mma3(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
-    const uint32_t a0 = __float_as_uint(a[0]), a1 = __float_as_uint(a[1]), a2 = __float_as_uint(a[2]), a3 = __float_as_uint(a[3]);
-    const uint32_t b0 = __float_as_uint(b[0]), b1 = __float_as_uint(b[1]);
-    mma_tf32_m16n8k8(c, tf32_lo(a[0]), tf32_lo(a[1]), tf32_lo(a[2]), tf32_lo(a[3]), b0, b1);
-    mma_tf32_m16n8k8(c, a0, a1, a2, a3, tf32_lo(b[0]), tf32_lo(b[1]));
-    mma_tf32_m16n8k8(c, a0, a1, a2, a3, b0, b1);
+// the same split on a register pair: two LOP3 + one packed subtract (sub.f32x2) instead of two LOP3 + two FADD
+__device__ __forceinline__ void tf32_lo2(uint32_t x0, uint32_t x1, uint32_t& l0, uint32_t& l1) {
+    uint64_t x, t, d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(x0), "r"(x1));
+    asm("and.b64 %0, %1, 0xffffe000ffffe000;" : "=l"(t) : "l"(x));
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(t));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(l0), "=r"(l1) : "l"(d));
+}
+// c = a * b (no accumulator to clear first)
+__device__ __forceinline__ void mma_tf32_m16n8k8_zero(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                      uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};\n"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+// c (+)= a * b with a (4 regs) and b (2 regs) given in fp32; 3xTF32.  ZERO: c is written, not accumulated into.
+template <bool ZERO>
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    uint32_t al[4], bl[2];
+    tf32_lo2(a[0], a[1], al[0], al[1]);
+    tf32_lo2(a[2], a[3], al[2], al[3]);
+    tf32_lo2(b[0], b[1], bl[0], bl[1]);
+    if (ZERO) mma_tf32_m16n8k8_zero(c, al[0], al[1], al[2], al[3], b[0], b[1]);
+    else mma_tf32_m16n8k8(c, al[0], al[1], al[2], al[3], b[0], b[1]);
+    mma_tf32_m16n8k8(c, a[0], a[1], a[2], a[3], bl[0], bl[1]);
+    mma_tf32_m16n8k8(c, a[0], a[1], a[2], a[3], b[0], b[1]);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -268,9 +287,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
 #pragma unroll 1
             for (int ii = 0; ii < DUB; ++ii) {
                 const int il = ib + ii;
-                float duf[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) duf[e] = 0.f;
+                float du0[4] = {0.f, 0.f, 0.f, 0.f}, du1[4] = {0.f, 0.f, 0.f, 0.f};       // du fragments of the two 16-sample halves
                 const float* stg = ring + sq * SF;          // this unit's stage: u tile, then coefficient rows
                 if (il < ni) mbar_wait(bar_full + 8 * sq, sph);
                 if (jvalid && il < ni) {
@@ -293,15 +310,18 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     __syncwarp();
                     if (il == ni - 1 && tile + 1 < p.nbt) load_x(tile + 1);
                     // ---- dW[d][k] += sum_b G[b][d] u[b][k] : 4 chunks of 8 samples, two accumulators
-                    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+                    float c0[4], c1[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float* gc = Gw + c * 128;
-                        const float a[4] = {gc[dwa0], gc[dwa0 ^ 8], gc[dwa2], gc[dwa2 ^ 8]};
+                        const uint32_t* gc = reinterpret_cast<const uint32_t*>(Gw + c * 128);
+                        const uint32_t a[4] = {gc[dwa0], gc[dwa0 ^ 8], gc[dwa2], gc[dwa2 ^ 8]};
                         // u[b][k] straight out of the stage: (k >> 2) * kGmUSkew + b * 4 + (k & 3)
-                        const float* ub = stg + (g >> 2) * kGmUSkew + (8 * c + t) * 4 + (g & 3);
-                        const float b[2] = {ub[0], ub[16]};
-                        if (c & 1) mma3(c1, a, b); else mma3(c0, a, b);
+                        const uint32_t* ub = reinterpret_cast<const uint32_t*>(stg + (g >> 2) * kGmUSkew + (8 * c + t) * 4 + (g & 3));
+                        const uint32_t b[2] = {ub[0], ub[16]};
+                        if (c == 0) mma3<true>(c0, a, b);
+                        else if (c == 1) mma3<true>(c1, a, b);
+                        else if (c & 1) mma3<false>(c1, a, b);
+                        else mma3<false>(c0, a, b);
                     }
                     float* dw = dWsm + (size_t)((il * JW + warp) * 32 + lane) * 4;     // lane-private: no hazard
                     float4 acc = *reinterpret_cast<float4*>(dw);
@@ -309,23 +329,18 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     *reinterpret_cast<float4*>(dw) = acc;
                     // ---- du[b][k] = sum_d G[b][d] W[k][d] : 2 x 16 samples, 2 K-steps of 8 dims
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        float cc[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint2 bw = *reinterpret_cast<const uint2*>(Wfrag + (size_t)((il * JW + warp) * 2 + ks) * 64 + lane * 2);
+                        const uint32_t b[2] = {bw.x, bw.y};
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            uint32_t ah[4], al[4];
+                        for (int mt = 0; mt < 2; ++mt) {
+                            uint32_t a[4];
                             asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3])
+                                         : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
                                          : "r"((ks ? lm_a1 : lm_a0) + mt * 1024) : "memory");
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) al[e] = tf32_lo(__uint_as_float(ah[e]));
-                            const float2 bh = *reinterpret_cast<const float2*>(Wfrag + (size_t)((il * JW + warp) * 2 + ks) * 64 + lane * 2);
-                            const float2 bl = make_float2(__uint_as_float(tf32_lo(bh.x)), __uint_as_float(tf32_lo(bh.y)));
-                            mma_tf32_m16n8k8(cc, al[0], al[1], al[2], al[3], __float_as_uint(bh.x), __float_as_uint(bh.y));
-                            mma_tf32_m16n8k8(cc, ah[0], ah[1], ah[2], ah[3], __float_as_uint(bl.x), __float_as_uint(bl.y));
-                            mma_tf32_m16n8k8(cc, ah[0], ah[1], ah[2], ah[3], __float_as_uint(bh.x), __float_as_uint(bh.y));
+                            if (ks == 0) { if (mt) mma3<true>(du1, a, b); else mma3<true>(du0, a, b); }
+                            else { if (mt) mma3<false>(du1, a, b); else mma3<false>(du0, a, b); }
                         }
-                        duf[mt * 4 + 0] = cc[0]; duf[mt * 4 + 1] = cc[1]; duf[mt * 4 + 2] = cc[2]; duf[mt * 4 + 3] = cc[3];
                     }
                 }
                 if (il < ni) {                              // every consumer warp releases every stage
@@ -334,8 +349,8 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     if (++sq == NS) { sq = 0; sph ^= 1; }
                 }
                 float* ds = dbuf + (size_t)((warp * DUB + ii) * 2) * 128 + lane * 4;   // [warp][ii][half][lane][4]
-                st4(ds, make_float4(duf[0], duf[1], duf[2], duf[3]));
-                st4(ds + 128, make_float4(duf[4], duf[5], duf[6], duf[7]));
+                st4(ds, make_float4(du0[0], du0[1], du0[2], du0[3]));
+                st4(ds + 128, make_float4(du1[0], du1[1], du1[2], du1[3]));
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_dufull + 8 * (rnd & 1));        // release: this warp's fragments are visible
