@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('CAPS_ROUTING_LIB') or os.path.join(HERE, 'libcaps_routing.so')   # env override: A/B experiments
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MARGIN_SCRATCH_FLOATS = 2048
 
 # every symbol include/caps_routing.h declares: name -> (restype, argtypes)
@@ -24,6 +24,8 @@ SYMBOLS = {
     'caps_margin_loss': (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'caps_squash': (_i, [_vp, _vp, _l, _i, _vp]),
     'caps_squash_backward': (_i, [_vp, _vp, _vp, _l, _i, _vp]),
+    'caps_primary_squash': (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    'caps_primary_squash_backward': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'caps_route_step_host_scratch_bytes': (_sz, [_i] * 6),
     'caps_route_step_host': (_i, [_vp] * 8 + [_sz] + [_i] * 6 + [_vp]),
     'caps_set_tuning': (_i, [ctypes.c_char_p, _i]),

@@ -4,14 +4,17 @@
 shape (reference models.py:46-83), so it drops into `models.CapsuleNet` / `models.DarkCapsuleNet`
 (assign `models.CapsuleLayer = CapsuleLayer` before building the model) with `main.py`,
 `loss_fns.py`, `predict_fns.py` unchanged.  The caps->caps branch runs in the hand-written
-sm_100a kernels; the conv->caps branch (n_nodes == -1) stays stock PyTorch (its squash uses the
-CUDA squash kernel when the input is a CUDA fp32 tensor).
+sm_100a kernels.  The conv->caps branch (n_nodes == -1, the step directly before the routing
+layer) runs its n_caps convolutions as ONE cuDNN convolution over the concatenated weights and
+does the views + cat + squash in one kernel (caps_primary_squash); on CPU tensors it is the
+reference's stock PyTorch code.
 
 PyTorch is plumbing here (device memory, streams, autograd graph); the arithmetic is in
 libcaps_routing.so.  There is no CPU fallback: CPU tensors on the routing branch raise.
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _cabi
 
@@ -163,6 +166,48 @@ class _SquashFn(torch.autograd.Function):
         return gx
 
 
+class _PrimarySquashFn(torch.autograd.Function):
+    """u [B, Cc*H*W, K] = squash_k(conv [B, K*Cc, H, W]): the primary-capsule tail (reference
+    models.py:81-82) through caps_primary_squash / caps_primary_squash_backward."""
+
+    @staticmethod
+    def forward(ctx, conv, n_caps):
+        L = _cabi.lib()
+        conv = conv.contiguous()
+        B, KC, H, W = conv.shape
+        Cc, HW = KC // n_caps, H * W
+        u = torch.empty((B, Cc * HW, n_caps), device=conv.device, dtype=torch.float32)
+        with torch.cuda.device(conv.device):
+            _cabi.check(L.caps_primary_squash(_ptr(conv), _ptr(u), B, n_caps, Cc, HW, _stream()), 'caps_primary_squash')
+        ctx.save_for_backward(conv)
+        ctx.n_caps = n_caps
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        (conv,) = ctx.saved_tensors
+        L = _cabi.lib()
+        B, KC, H, W = conv.shape
+        K = ctx.n_caps
+        dconv = torch.empty_like(conv)
+        with torch.cuda.device(conv.device):
+            _cabi.check(L.caps_primary_squash_backward(_ptr(conv), _ptr(du.contiguous()), _ptr(dconv), B, K, KC // K, H * W,
+                                                       _stream()), 'caps_primary_squash_backward')
+        return dconv, None
+
+
+def primary_capsules(x, convs):
+    """x [B,in_C,H,W] through the K capsule convolutions `convs` (an nn.ModuleList of identical-shape
+    Conv2d) -> squashed u [B, out_C*H'*W', K]: one convolution over the concatenated weights (the
+    parameters stay K separate tensors, so state_dict names/shapes are the reference's), then one
+    kernel for the views + cat + squash."""
+    c0 = convs[0]
+    w = torch.cat([m.weight for m in convs], dim=0)
+    b = None if c0.bias is None else torch.cat([m.bias for m in convs], dim=0)
+    conv = F.conv2d(x, w, b, stride=c0.stride, padding=c0.padding, dilation=c0.dilation, groups=c0.groups)
+    return _PrimarySquashFn.apply(conv, len(convs))
+
+
 def dynamic_routing(u, route_weights, n_iter=3, return_couplings=False):
     """u [B,N,K], route_weights [1,N,C,K,D]  ->  v [B,C,D] (and the last couplings c [B,N,C])."""
     return _RoutingFn.apply(u, route_weights, int(n_iter), bool(return_couplings))
@@ -186,7 +231,7 @@ class CapsuleLayer(nn.Module):
         self.n_caps = n_caps
         if n_nodes != -1:   # caps -> caps: the routing branch (models.py:56-58)
             self.route_weights = nn.Parameter(0.1 * torch.randn(1, n_nodes, n_caps, in_C, out_C))
-        else:               # conv -> caps: primary capsules (models.py:59-62), stock PyTorch
+        else:               # conv -> caps: primary capsules (models.py:59-62), same modules as the reference
             self.capsules = nn.ModuleList(
                 [nn.Conv2d(in_C, out_C, kernel, stride=stride) for _ in range(n_caps)])
 
@@ -201,7 +246,9 @@ class CapsuleLayer(nn.Module):
             v = dynamic_routing(x, self.route_weights, self.n_iter)       # [B,C,D]
             B, C, D = v.shape
             return v.view(B, 1, C, 1, D)                                   # reference output shape
-        outs = [cap(x).view(x.size(0), -1, 1) for cap in self.capsules]
+        if x.is_cuda and x.dtype == torch.float32 and len(self.capsules) <= 16:
+            return primary_capsules(x, self.capsules)
+        outs = [cap(x).view(x.size(0), -1, 1) for cap in self.capsules]     # reference models.py:81-82
         return self.squash(torch.cat(outs, dim=-1))
 
     def forward_margin_loss(self, x, y):

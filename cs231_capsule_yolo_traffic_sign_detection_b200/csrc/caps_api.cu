@@ -444,6 +444,37 @@ int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, 
     return 0;
 }
 
+int caps_primary_squash(const float* conv, float* u, int B, int n_caps, int Cc, int HW, void* stream) {
+    if (!conv || !u || B < 0 || n_caps <= 0 || n_caps > 16 || Cc <= 0 || HW <= 0)
+        return fail(CAPS_E_BADARG, "caps_primary_squash: bad argument (n_caps must be in 1..16)");
+    if (misaligned(u)) return fail(CAPS_E_BADARG, "caps_primary_squash: u must be 16-byte aligned");
+    const long total = (long)B * Cc * HW;
+    if (total == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        LaunchScope ls_(kcLayout, st);
+        if (n_caps <= 8) k_primary_squash<8><<<cdiv(total, 256), 256, 0, st>>>(conv, u, total, n_caps, Cc, HW);
+        else k_primary_squash<16><<<cdiv(total, 256), 256, 0, st>>>(conv, u, total, n_caps, Cc, HW);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int caps_primary_squash_backward(const float* conv, const float* du, float* dconv, int B, int n_caps, int Cc, int HW, void* stream) {
+    if (!conv || !du || !dconv || B < 0 || n_caps <= 0 || n_caps > 16 || Cc <= 0 || HW <= 0)
+        return fail(CAPS_E_BADARG, "caps_primary_squash_backward: bad argument (n_caps must be in 1..16)");
+    const long total = (long)B * Cc * HW;
+    if (total == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        LaunchScope ls_(kcLayout, st);
+        if (n_caps <= 8) k_primary_squash_bwd<8><<<cdiv(total, 256), 256, 0, st>>>(conv, du, dconv, total, n_caps, Cc, HW);
+        else k_primary_squash_bwd<16><<<cdiv(total, 256), 256, 0, st>>>(conv, du, dconv, total, n_caps, Cc, HW);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- host-buffer step ------------------------------------------------------------------------
 // The batch is cut into up to three micro-batches (B/8, 3B/8, B/2, multiples of 128) so that the
 // host->device copy of micro-batch m+1 (on an internal copy stream) runs under the kernels of

@@ -818,6 +818,69 @@ static __global__ void k_squash_rows_bwd(const float* __restrict__ x, const floa
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// primary-capsule tail (reference models.py:81-82): conv [B][K*Cc][HW] (ONE convolution whose output channels
+// are the K capsule convolutions' channels, capsule-major) -> u [B][Cc*HW][K] = squash over k.  The reference's
+// K x view, cat(dim=-1) and 7-op squash become one pass: thread <-> (b, c, hw) reads K values that are
+// coalesced across hw and writes K consecutive floats.
+// ---------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void k_primary_squash(const float* __restrict__ conv, float* __restrict__ u, long total, int K, int Cc, int HW) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;        // (b, c, hw), hw fastest
+    if (idx >= total) return;
+    const int hw = (int)(idx % HW);
+    const long bc = idx / HW;
+    const int c = (int)(bc % Cc);
+    const long b = bc / Cc;
+    const float* src = conv + ((size_t)b * K * Cc + c) * HW + hw;
+    float x[KMAX];
+    float n2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        x[k] = k < K ? __ldg(src + (size_t)k * Cc * HW) : 0.f;
+        n2 = fmaf(x[k], x[k], n2);
+    }
+    const float scale = n2 / (1.f + n2), rn = sqrtf(n2);
+    float* dst = u + (size_t)idx * K;
+    if (KMAX == 8 && K == 8) {
+        st4(dst, make_float4(scale * x[0] / rn, scale * x[1] / rn, scale * x[2] / rn, scale * x[3] / rn));
+        st4(dst + 4, make_float4(scale * x[4] / rn, scale * x[5] / rn, scale * x[6] / rn, scale * x[7] / rn));
+    } else {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) dst[k] = scale * x[k] / rn;
+    }
+}
+
+// dconv [B][K*Cc][HW] = squash'(conv) applied to du [B][Cc*HW][K] (same formula as k_squash_rows_bwd)
+template <int KMAX>
+__global__ void k_primary_squash_bwd(const float* __restrict__ conv, const float* __restrict__ du, float* __restrict__ dconv,
+                                     long total, int K, int Cc, int HW) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int hw = (int)(idx % HW);
+    const long bc = idx / HW;
+    const int c = (int)(bc % Cc);
+    const long b = bc / Cc;
+    const size_t o = ((size_t)b * K * Cc + c) * HW + hw;
+    const float* g = du + (size_t)idx * K;
+    float x[KMAX], gy[KMAX];
+    float n2 = 0.f, sdv = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        x[k] = k < K ? __ldg(conv + o + (size_t)k * Cc * HW) : 0.f;
+        gy[k] = k < K ? __ldg(g + k) : 0.f;
+        n2 = fmaf(x[k], x[k], n2);
+        sdv = fmaf(x[k], gy[k], sdv);
+    }
+    const float n = sqrtf(n2);
+    const float a = n / (1.f + n2);
+    const float bb = sdv * (1.f - n2) / (n * (1.f + n2) * (1.f + n2));
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < K) dconv[o + (size_t)k * Cc * HW] = fmaf(a, gy[k], bb * x[k]);
+}
+
 // fp32 FMA-pipe peak probe: 16 independent FFMA chains per thread (bench.py's FMA roofline
 // denominator; MEASURED_PEAKS.json has no fp32 figure).
 static __global__ void k_fma_peak(float* __restrict__ sink, int iters, float m0, float c0) {

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define CAPS_ABI_VERSION 1
+#define CAPS_ABI_VERSION 2
 
 #define CAPS_E_BADARG     (-1)   /* null pointer / non-positive dim / misaligned pointer        */
 #define CAPS_E_UNSUPPORTED (-2)  /* K != 8, D > 48, R > 5, C > 1024: shapes with no kernel       */
@@ -91,6 +91,18 @@ int caps_margin_loss(const float* v, const int64_t* y, float scale, float* loss,
 int caps_squash(const float* x, float* y, long rows, int D, void* stream);
 /* its backward: dx = d squash(x)/dx applied to dy. */
 int caps_squash_backward(const float* x, const float* dy, float* dx, long rows, int D, void* stream);
+
+/* Primary-capsule tail, the step directly before the routing layer (SURVEY.md section 8(f) row 1;
+ * reference models.py:81-82: `[cap(x).view(B,-1,1) for cap in self.capsules]`, `torch.cat(dim=-1)`,
+ * `squash`).  `conv` [B][n_caps*Cc][HW] is the output of ONE convolution whose weight is the n_caps
+ * capsule convolutions' weights concatenated along the output-channel axis (channel = k*Cc + c);
+ * `u` [B][Cc*HW][n_caps] is the routing layer's input: u[b][c*HW + hw][k] = squash over k of
+ * conv[b][k*Cc + c][hw] (reference models.py:64-67, no epsilon).  The K views, the cat and the
+ * seven elementwise ops of squash are one pass over the data.  Backward: dconv from du.
+ * n_caps <= 16; u 16-byte aligned. */
+int caps_primary_squash(const float* conv, float* u, int B, int n_caps, int Cc, int HW, void* stream);
+int caps_primary_squash_backward(const float* conv, const float* du, float* dconv,
+                                 int B, int n_caps, int Cc, int HW, void* stream);
 
 /* HOST-buffer step, the end-to-end call: copies u (and y) host->device, runs forward, margin
  * loss, fused backward, and copies loss (and, if non-NULL, v / du / dW) device->host, all on

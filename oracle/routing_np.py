@@ -9,6 +9,7 @@ of the caps->caps branch of the reference `CapsuleLayer`:
 
     reference models.py:64-67   squash
     reference models.py:70-79   prediction vectors + routing loop
+    reference models.py:81-82   primary-capsule tail (views + cat + squash), the step before the routing layer
     reference models.py:116-117 class scores (norm of the class capsules)
     reference loss_fns.py:11-17,23  margin loss (recon term excluded: it is not on the path)
 
@@ -35,6 +36,22 @@ def squash_bwd(s, dv):
     n = np.sqrt(n2)
     sdv = (s * dv).sum(-1, keepdims=True)
     return dv * n / (1.0 + n2) + s * sdv * (1.0 - n2) / (n * (1.0 + n2) ** 2)
+
+
+def primary_tail(conv, n_caps):
+    """reference models.py:81-82 -- `[cap(x).view(B,-1,1) for cap in capsules]`, cat(dim=-1), squash.
+    conv [B, n_caps*Cc, H, W] holds the n_caps conv outputs capsule-major (channel = k*Cc + c);
+    returns u [B, Cc*H*W, n_caps]."""
+    B, KC, H, W = conv.shape
+    pre = conv.reshape(B, n_caps, (KC // n_caps) * H * W).transpose(0, 2, 1)
+    return squash(pre)
+
+
+def primary_tail_bwd(conv, du, n_caps):
+    """gradient of primary_tail w.r.t. conv, same layout as conv."""
+    B, KC, H, W = conv.shape
+    pre = conv.reshape(B, n_caps, (KC // n_caps) * H * W).transpose(0, 2, 1)
+    return squash_bwd(pre, du).transpose(0, 2, 1).reshape(conv.shape)
 
 
 def softmax_c(b):

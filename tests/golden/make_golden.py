@@ -97,11 +97,50 @@ def run_reference(ref_models, ref_loss, u, W, y, R, dtype):
                 du=ut.grad.numpy(), dW=layer.route_weights.grad[0].numpy())
 
 
+def make_primary(ref_models):
+    """Primary-capsule branch (reference models.py:59-62, 81-82), the step before the routing layer:
+    K convolutions -> view -> cat(dim=-1) -> squash.  Stores inputs, the K conv outputs stacked
+    capsule-major, the layer output, and autograd's gradients for a seeded upstream gradient."""
+    B, Cin, H, K, Cc, kern, stride = 3, 6, 14, 8, 5, 4, 2
+    g = torch.Generator().manual_seed(31)
+    layer = ref_models.CapsuleLayer(P(), n_caps=K, n_nodes=-1, in_C=Cin, out_C=Cc, kernel=kern, stride=stride)
+    with torch.no_grad():
+        for m in layer.capsules:
+            m.weight.copy_(0.2 * torch.randn(m.weight.shape, generator=g))
+            m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    x = torch.randn(B, Cin, H, H, generator=g).requires_grad_(True)
+    outs = []
+    def keep(mod, inp, out):
+        out.retain_grad()
+        outs.append(out)
+    hooks = [m.register_forward_hook(keep) for m in layer.capsules]
+    u = layer(x)                                              # [B, Cc*H'*W', K]
+    for h in hooks:
+        h.remove()
+    du = torch.randn(u.shape, generator=g)
+    u.backward(du)
+    conv = torch.cat(outs, dim=1)                             # [B, K*Cc, H', W'], channel = k*Cc + c
+    dconv = torch.cat([o.grad for o in outs], dim=1)
+    blob = dict(dims=np.array([B, Cin, H, K, Cc, kern, stride], dtype=np.int64),
+                x=x.detach().numpy(), weight=np.stack([m.weight.detach().numpy() for m in layer.capsules]),
+                bias=np.stack([m.bias.detach().numpy() for m in layer.capsules]),
+                conv=conv.detach().numpy(), u=u.detach().numpy(), du=du.numpy(), dconv=dconv.numpy(),
+                dx=x.grad.numpy(), dweight=np.stack([m.weight.grad.numpy() for m in layer.capsules]),
+                dbias=np.stack([m.bias.grad.numpy() for m in layer.capsules]))
+    path = os.path.join(HERE, 'primary_caps.npz')
+    np.savez_compressed(path, **blob)
+    print('%-20s conv %s -> u %s -> %s (%d KB)' % ('primary_caps', tuple(conv.shape), tuple(u.shape),
+                                                os.path.basename(path), os.path.getsize(path) // 1024))
+
+
 def main():
     from oracle import routing_np as onp
     ref_models, ref_loss = import_reference()
     torch.manual_seed(0)
     torch.set_num_threads(1)   # one thread: reduction order (hence the fp32 bits) is reproducible
+    make_primary(ref_models)
+    if '--primary-only' in sys.argv:
+        return
     for name, (B, N, C, K, D, R, seed, full) in CASES.items():
         u, W, y = onp.make_inputs(B, N, C, K, D, seed=seed)
         r32 = run_reference(ref_models, ref_loss, u, W, y, R, torch.float32)

@@ -111,3 +111,18 @@ def test_c_oracle_matches_reference(name):
     assert rel_err(r['v'], g['v64']) < 1e-5
     assert rel_err(r['du'], g['du64']) < 1e-4
     assert rel_err(r['dW'].reshape(-1)[::st], g['dW64_probe']) < 1e-4
+
+
+def test_primary_tail_matches_reference():
+    """The primary-capsule tail (reference models.py:81-82: K views + cat + squash) and its gradient,
+    against the reference layer's own output / autograd (tests/golden/primary_caps.npz)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import routing_np as onp
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'primary_caps.npz')))
+    K = int(g['dims'][3])
+    u = onp.primary_tail(g['conv'].astype(np.float64), K)
+    assert u.shape == g['u'].shape
+    assert rel_err(u, g['u']) < 1e-6
+    dconv = onp.primary_tail_bwd(g['conv'].astype(np.float64), g['du'].astype(np.float64), K)
+    assert rel_err(dconv, g['dconv']) < 1e-6

@@ -315,3 +315,59 @@ def test_squash_kernel(capsb):
     y.backward(gy)
     gref = onp.squash_bwd(x.detach().cpu().numpy().astype(np.float64), gy.cpu().numpy().astype(np.float64))
     assert rel_err(x.grad.cpu().numpy(), gref) < 1e-5
+
+
+def test_primary_capsule_tail_kernel(capsb):
+    """caps_primary_squash / _backward (the K views + cat + squash of reference models.py:81-82 in one
+    pass) against the reference's own output and autograd gradient, and against the oracle at the
+    real CapsuleNet shape (8 capsules x 16 channels x 9x9)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import routing_np as onp
+    from cs231_capsule_yolo_traffic_sign_detection_b200.capsule import _PrimarySquashFn
+    dev = torch.device('cuda')
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'primary_caps.npz')))
+    K = int(g['dims'][3])
+    conv = torch.from_numpy(g['conv']).to(dev).requires_grad_(True)
+    u = _PrimarySquashFn.apply(conv, K)
+    assert rel_err(u.detach().cpu().numpy(), g['u']) < 1e-6
+    u.backward(torch.from_numpy(g['du']).to(dev))
+    assert rel_err(conv.grad.cpu().numpy(), g['dconv']) < 1e-5
+    rng = np.random.default_rng(5)
+    for (B, Kc, Cc, H) in ((33, 8, 16, 9), (2, 3, 7, 5), (4, 12, 4, 3)):
+        cv = rng.standard_normal((B, Kc * Cc, H, H)).astype(np.float32)
+        du = rng.standard_normal((B, Cc * H * H, Kc)).astype(np.float32)
+        ct = torch.from_numpy(cv).to(dev).requires_grad_(True)
+        ut = _PrimarySquashFn.apply(ct, Kc)
+        assert rel_err(ut.detach().cpu().numpy(), onp.primary_tail(cv.astype(np.float64), Kc)) < 1e-6
+        ut.backward(torch.from_numpy(du).to(dev))
+        assert rel_err(ct.grad.cpu().numpy(), onp.primary_tail_bwd(cv.astype(np.float64), du.astype(np.float64), Kc)) < 1e-5
+
+
+def test_primary_capsule_layer_matches_reference(capsb):
+    """The conv->caps branch of the drop-in layer (ONE convolution over the concatenated weights + the
+    fused tail) against the reference layer's output and autograd gradients; the parameters stay
+    K separate Conv2d modules (state_dict names and shapes of the reference)."""
+    import os
+    from conftest import GOLDEN_DIR
+    dev = torch.device('cuda')
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'primary_caps.npz')))
+    B, Cin, H, K, Cc, kern, stride = [int(v) for v in g['dims']]
+    layer = capsb.CapsuleLayer(None, n_caps=K, n_nodes=-1, in_C=Cin, out_C=Cc, kernel=kern, stride=stride).to(dev)
+    assert sorted(layer.state_dict().keys()) == sorted(
+        ['capsules.%d.%s' % (k, n) for k in range(K) for n in ('weight', 'bias')])
+    with torch.no_grad():
+        for k, m in enumerate(layer.capsules):
+            m.weight.copy_(torch.from_numpy(g['weight'][k]))
+            m.bias.copy_(torch.from_numpy(g['bias'][k]))
+    torch.backends.cudnn.allow_tf32 = False          # fp32 convolution like the reference's
+    x = torch.from_numpy(g['x']).to(dev).requires_grad_(True)
+    u = layer(x)
+    assert tuple(u.shape) == tuple(g['u'].shape)
+    assert rel_err(u.detach().cpu().numpy(), g['u']) < 1e-5
+    u.backward(torch.from_numpy(g['du']).to(dev))
+    assert rel_err(x.grad.cpu().numpy(), g['dx']) < 1e-4
+    dw = np.stack([m.weight.grad.cpu().numpy() for m in layer.capsules])
+    db = np.stack([m.bias.grad.cpu().numpy() for m in layer.capsules])
+    assert rel_err(dw, g['dweight']) < 1e-4
+    assert rel_err(db, g['dbias']) < 1e-4
