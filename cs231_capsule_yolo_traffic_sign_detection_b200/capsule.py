@@ -208,6 +208,42 @@ def primary_capsules(x, convs):
     return _PrimarySquashFn.apply(conv, len(convs))
 
 
+class _DarkRegroupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, G):
+        L = _cabi.lib()
+        x = x.contiguous()
+        B, Cch = x.shape[0], x.shape[1]
+        u = torch.empty((G * B, 2 * Cch, 8), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _cabi.check(L.caps_dark_regroup(_ptr(x), _ptr(u), B, Cch, G, _stream()), 'caps_dark_regroup')
+        ctx.shape, ctx.G = x.shape, G
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        L = _cabi.lib()
+        dx = torch.empty(ctx.shape, device=du.device, dtype=torch.float32)
+        with torch.cuda.device(du.device):
+            _cabi.check(L.caps_dark_regroup_backward(_ptr(du.contiguous()), _ptr(dx), ctx.shape[0], ctx.shape[1], ctx.G, _stream()),
+                        'caps_dark_regroup_backward')
+        return dx, None
+
+
+def dark_regroup(x, n_grid):
+    """DarkCapsuleNet's cell regroup (reference models.py:393-399) in one kernel: feature map
+    x [B, Cch, H, W] with H*W == 16*n_grid**2 -> u [n_grid**2 * B, 2*Cch, 8], the routing layer's
+    input (cell-major batch: row q*B + b).  Same values and order as the reference's
+    view / chunk / permute / contiguous / cat sequence."""
+    G = int(n_grid) ** 2
+    if x.dim() != 4 or x.shape[2] * x.shape[3] != 16 * G or x.shape[1] % 8:
+        raise RuntimeError('dark_regroup: expected [B, Cch (multiple of 8), H, W] with H*W == 16*n_grid^2, got %s'
+                           % (tuple(x.shape),))
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError('dark_regroup runs on CUDA fp32 tensors only')
+    return _DarkRegroupFn.apply(x, G)
+
+
 def dynamic_routing(u, route_weights, n_iter=3, return_couplings=False):
     """u [B,N,K], route_weights [1,N,C,K,D]  ->  v [B,C,D] (and the last couplings c [B,N,C])."""
     return _RoutingFn.apply(u, route_weights, int(n_iter), bool(return_couplings))

@@ -475,6 +475,28 @@ int caps_primary_squash_backward(const float* conv, const float* du, float* dcon
     return 0;
 }
 
+int caps_dark_regroup(const float* x, float* u, int B, int Cch, int G, void* stream) {
+    if (!x || !u || B < 0 || Cch <= 0 || (Cch & 7) || G <= 0) return fail(CAPS_E_BADARG, "caps_dark_regroup: bad argument (Cch must be a multiple of 8)");
+    if (misaligned(u)) return fail(CAPS_E_BADARG, "caps_dark_regroup: u must be 16-byte aligned");
+    const long total = (long)B * (Cch / 8) * 16 * G;
+    if (total == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { LaunchScope ls_(kcLayout, st); k_dark_regroup<false><<<cdiv(total, 256), 256, 0, st>>>(x, u, total, B, Cch, G); }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+int caps_dark_regroup_backward(const float* du, float* dx, int B, int Cch, int G, void* stream) {
+    if (!du || !dx || B < 0 || Cch <= 0 || (Cch & 7) || G <= 0) return fail(CAPS_E_BADARG, "caps_dark_regroup_backward: bad argument (Cch must be a multiple of 8)");
+    if (misaligned(du)) return fail(CAPS_E_BADARG, "caps_dark_regroup_backward: du must be 16-byte aligned");
+    const long total = (long)B * (Cch / 8) * 16 * G;
+    if (total == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { LaunchScope ls_(kcLayout, st); k_dark_regroup<true><<<cdiv(total, 256), 256, 0, st>>>(du, dx, total, B, Cch, G); }
+    LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- host-buffer step ------------------------------------------------------------------------
 // The batch is cut into up to three micro-batches (B/8, 3B/8, B/2, multiples of 128) so that the
 // host->device copy of micro-batch m+1 (on an internal copy stream) runs under the kernels of

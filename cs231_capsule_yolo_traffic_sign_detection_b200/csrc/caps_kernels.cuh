@@ -881,6 +881,39 @@ __global__ void k_primary_squash_bwd(const float* __restrict__ conv, const float
         if (k < K) dconv[o + (size_t)k * Cc * HW] = fmaf(a, gy[k], bb * x[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// DarkCapsuleNet cell regroup (reference models.py:393-399): feature map x [B][Cch][16*G] (the 28x28 map viewed as
+// [4][4*G]) -> u [G*B][2*Cch][8] for the routing layer:
+//     u[q*B + b][(a*4 + t)*(Cch/8) + ch/8][ch%8] = x[b][ch][a*4*G + 4*q + t]        q < G, a < 4, t < 4
+// i.e. the reference's view + chunk(G) + G x (permute, contiguous, view, unsqueeze) + cat in one pass.
+// thread <-> (b, ch/8, s): the 8 reads are coalesced across s, the write is one 32-byte sector.
+// BWD: the same index map, gradient flowing from du back into dx.
+// ---------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void k_dark_regroup(const float* __restrict__ src, float* __restrict__ dst, long total, int B, int Cch, int G) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;        // (b, c8, s), s fastest
+    if (idx >= total) return;
+    const int S = 16 * G, C8 = Cch >> 3;
+    const int sp = (int)(idx % S);
+    const long bc = idx / S;
+    const int c8 = (int)(bc % C8);
+    const long b = bc / C8;
+    const int a = sp / (4 * G), r = sp % (4 * G), q = r >> 2, t = r & 3;
+    const size_t xo = ((size_t)b * Cch + c8 * 8) * S + sp;                                  // x[b][8 c8 + k][sp], k stride S
+    const size_t uo = (((size_t)q * B + b) * (2 * Cch) + (size_t)(a * 4 + t) * C8 + c8) * 8; // u[q B + b][n][0..7]
+    if (!BWD) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(src + xo + (size_t)k * S);
+        st4(dst + uo, make_float4(v[0], v[1], v[2], v[3]));
+        st4(dst + uo + 4, make_float4(v[4], v[5], v[6], v[7]));
+    } else {
+        const float4 lo = ldg4(src + uo), hi = ldg4(src + uo + 4);
+        dst[xo] = lo.x; dst[xo + (size_t)S] = lo.y; dst[xo + (size_t)2 * S] = lo.z; dst[xo + (size_t)3 * S] = lo.w;
+        dst[xo + (size_t)4 * S] = hi.x; dst[xo + (size_t)5 * S] = hi.y; dst[xo + (size_t)6 * S] = hi.z; dst[xo + (size_t)7 * S] = hi.w;
+    }
+}
+
 // fp32 FMA-pipe peak probe: 16 independent FFMA chains per thread (bench.py's FMA roofline
 // denominator; MEASURED_PEAKS.json has no fp32 figure).
 static __global__ void k_fma_peak(float* __restrict__ sink, int iters, float m0, float c0) {

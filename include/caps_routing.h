@@ -104,6 +104,16 @@ int caps_primary_squash(const float* conv, float* u, int B, int n_caps, int Cc, 
 int caps_primary_squash_backward(const float* conv, const float* du, float* dconv,
                                  int B, int n_caps, int Cc, int HW, void* stream);
 
+/* DarkCapsuleNet cell regroup, the step directly before the routing layer in that model (SURVEY.md
+ * section 8(f) row 2; reference models.py:393-399: `x.view(B,256,4,4*g*g)`, `torch.chunk(.., g*g, 3)`,
+ * then per chunk `permute(0,2,3,1).contiguous().view(B,-1,8).unsqueeze(0)`, `torch.cat(.., 0)`,
+ * `.view(-1,512,8)`).  x [B][Cch][16*G] (G = g*g cells), u [G*B][2*Cch][8]:
+ *   u[q*B + b][(a*4 + t)*(Cch/8) + ch/8][ch%8] = x[b][ch][a*4*G + 4*q + t],  q < G, a < 4, t < 4.
+ * One pass instead of ~2 G + 2 kernels and two full copies; the backward is the inverse map.
+ * Cch % 8 == 0; u / du 16-byte aligned. */
+int caps_dark_regroup(const float* x, float* u, int B, int Cch, int G, void* stream);
+int caps_dark_regroup_backward(const float* du, float* dx, int B, int Cch, int G, void* stream);
+
 /* HOST-buffer step, the end-to-end call: copies u (and y) host->device, runs forward, margin
  * loss, fused backward, and copies loss (and, if non-NULL, v / du / dW) device->host, all on
  * `stream`, then synchronises that stream.  u_host/y_host/..._host are HOST pointers (pinned for

@@ -10,6 +10,7 @@ of the caps->caps branch of the reference `CapsuleLayer`:
     reference models.py:64-67   squash
     reference models.py:70-79   prediction vectors + routing loop
     reference models.py:81-82   primary-capsule tail (views + cat + squash), the step before the routing layer
+    reference models.py:393-399 DarkCapsuleNet cell regroup, the step before the routing layer in that model
     reference models.py:116-117 class scores (norm of the class capsules)
     reference loss_fns.py:11-17,23  margin loss (recon term excluded: it is not on the path)
 
@@ -52,6 +53,22 @@ def primary_tail_bwd(conv, du, n_caps):
     B, KC, H, W = conv.shape
     pre = conv.reshape(B, n_caps, (KC // n_caps) * H * W).transpose(0, 2, 1)
     return squash_bwd(pre, du).transpose(0, 2, 1).reshape(conv.shape)
+
+
+def dark_regroup(x, n_grid):
+    """reference models.py:393-399 -- view(B,Cch,4,4g^2), chunk(g^2, dim 3), per chunk
+    permute(0,2,3,1).contiguous().view(B,-1,8), stacked cell-major: [g^2*B, 2*Cch, 8]."""
+    B, Cch = x.shape[0], x.shape[1]
+    G = n_grid * n_grid
+    xv = x.reshape(B, Cch, 4, G, 4)                        # [b, ch, a, q, t]
+    return np.ascontiguousarray(xv.transpose(3, 0, 2, 4, 1)).reshape(G * B, 2 * Cch, 8)   # [q, b, a, t, ch]
+
+
+def dark_regroup_bwd(du, B, Cch, n_grid):
+    """inverse map: gradient w.r.t. x [B, Cch, 16 g^2] from du [g^2*B, 2*Cch, 8]."""
+    G = n_grid * n_grid
+    dv = du.reshape(G, B, 4, 4, Cch)                       # [q, b, a, t, ch]
+    return np.ascontiguousarray(dv.transpose(1, 4, 2, 0, 3)).reshape(B, Cch, 16 * G)      # [b, ch, a, q, t]
 
 
 def softmax_c(b):

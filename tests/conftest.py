@@ -16,8 +16,8 @@ def pytest_configure(config):
 
 
 def golden_names():
-    # routing-layer fixtures; primary_caps.npz (the step before the routing layer) has its own tests
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith('primary'))
+    # routing-layer fixtures; primary_caps.npz / dark_regroup.npz (the steps before the routing layer) have their own tests
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith('.npz') and not f.startswith(('primary', 'dark_regroup')))
 
 
 def load_golden(name):
@@ -37,3 +37,10 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def dark_pattern(shape, mul, mod):
+    """integer-valued fp32 test pattern used by tests/golden/make_golden.py::make_dark_regroup
+    (exact through any permutation; inputs are regenerated from it, the fixture stores outputs only)"""
+    n = int(np.prod(shape))
+    return ((np.arange(n, dtype=np.int64) * mul) % mod).astype(np.float32).reshape(shape)

@@ -133,12 +133,45 @@ def make_primary(ref_models):
                                                 os.path.basename(path), os.path.getsize(path) // 1024))
 
 
+def dark_pattern(shape, mul, mod):
+    """integer-valued fp32 test pattern (exact through any permutation, compresses well)"""
+    n = int(np.prod(shape))
+    return ((np.arange(n, dtype=np.int64) * mul) % mod).astype(np.float32).reshape(shape)
+
+
+def make_dark_regroup(ref_models):
+    """DarkCapsuleNet.forward's cell regroup (reference models.py:393-399), run through the UNMODIFIED forward: the
+    backbone `model.conv` is swapped for nn.Identity() so that a synthetic [B,256,28,28] feature map reaches the
+    regroup lines; a forward pre-hook on the routing layer captures what they hand to it."""
+    B, g = 2, 7
+    params = P()
+    params.n_grid = g
+    params.n_classes = 43
+    params.dropout = 0.0
+    model = ref_models.DarkCapsuleNet(params)
+    model.conv = torch.nn.Identity()
+    x = torch.from_numpy(dark_pattern((B, 256, 28, 28), 7919, 8191)).requires_grad_(True)
+    seen = []
+    h = model.traffic_sign_capsules.register_forward_pre_hook(lambda mod, inp: seen.append(inp[0]))
+    out = model(x)
+    h.remove()
+    u = seen[0]                                               # [g*g*B, 512, 8]
+    du = torch.from_numpy(dark_pattern(tuple(u.shape), 104729, 8179))
+    u.backward(du)
+    path = os.path.join(HERE, 'dark_regroup.npz')
+    np.savez_compressed(path, dims=np.array([B, 256, g], dtype=np.int64), out_shape=np.array(out.shape, dtype=np.int64),
+                        u=u.detach().numpy().astype(np.uint16), dx=x.grad.numpy().astype(np.uint16))
+    print('%-20s x %s -> u %s -> %s (%d KB)' % ('dark_regroup', tuple(x.shape), tuple(u.shape), os.path.basename(path),
+                                                os.path.getsize(path) // 1024))
+
+
 def main():
     from oracle import routing_np as onp
     ref_models, ref_loss = import_reference()
     torch.manual_seed(0)
     torch.set_num_threads(1)   # one thread: reduction order (hence the fp32 bits) is reproducible
     make_primary(ref_models)
+    make_dark_regroup(ref_models)
     if '--primary-only' in sys.argv:
         return
     for name, (B, N, C, K, D, R, seed, full) in CASES.items():

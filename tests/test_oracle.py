@@ -126,3 +126,19 @@ def test_primary_tail_matches_reference():
     assert rel_err(u, g['u']) < 1e-6
     dconv = onp.primary_tail_bwd(g['conv'].astype(np.float64), g['du'].astype(np.float64), K)
     assert rel_err(dconv, g['dconv']) < 1e-6
+
+
+def test_dark_regroup_matches_reference():
+    """DarkCapsuleNet's cell regroup (reference models.py:393-399) and its gradient: bit-exact against
+    what the unmodified DarkCapsuleNet.forward handed to its routing layer (tests/golden/dark_regroup.npz)."""
+    import os
+    from conftest import GOLDEN_DIR, dark_pattern
+    from oracle import routing_np as onp
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'dark_regroup.npz')))
+    B, Cch, grid = [int(v) for v in g['dims']]
+    x = dark_pattern((B, Cch, 4 * grid, 4 * grid), 7919, 8191)
+    u = onp.dark_regroup(x, grid)
+    assert np.array_equal(u, g['u'].astype(np.float32))
+    du = dark_pattern(u.shape, 104729, 8179)
+    dx = onp.dark_regroup_bwd(du, B, Cch, grid)
+    assert np.array_equal(dx.reshape(x.shape), g['dx'].astype(np.float32))

@@ -371,3 +371,33 @@ def test_primary_capsule_layer_matches_reference(capsb):
     db = np.stack([m.bias.grad.cpu().numpy() for m in layer.capsules])
     assert rel_err(dw, g['dweight']) < 1e-4
     assert rel_err(db, g['dbias']) < 1e-4
+
+
+def test_dark_regroup_kernel(capsb):
+    """caps_dark_regroup / _backward: bit-exact against the reference's own regroup (fixture) and, on
+    random data and other shapes, against the oracle."""
+    import os
+    from conftest import GOLDEN_DIR, dark_pattern
+    from oracle import routing_np as onp
+    dev = torch.device('cuda')
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'dark_regroup.npz')))
+    B, Cch, grid = [int(v) for v in g['dims']]
+    x = torch.from_numpy(dark_pattern((B, Cch, 4 * grid, 4 * grid), 7919, 8191)).to(dev).requires_grad_(True)
+    u = capsb.dark_regroup(x, grid)
+    assert tuple(u.shape) == (grid * grid * B, 2 * Cch, 8)
+    assert np.array_equal(u.detach().cpu().numpy(), g['u'].astype(np.float32))
+    u.backward(torch.from_numpy(dark_pattern(tuple(u.shape), 104729, 8179)).to(dev))
+    assert np.array_equal(x.grad.cpu().numpy(), g['dx'].astype(np.float32))
+    rng = np.random.default_rng(3)
+    for (B2, C2, g2) in ((5, 64, 3), (1, 8, 1), (32, 256, 7)):
+        xv = rng.standard_normal((B2, C2, 4 * g2, 4 * g2)).astype(np.float32)
+        xt = torch.from_numpy(xv).to(dev).requires_grad_(True)
+        ut = capsb.dark_regroup(xt, g2)
+        assert np.array_equal(ut.detach().cpu().numpy(), onp.dark_regroup(xv, g2))
+        duv = rng.standard_normal(tuple(ut.shape)).astype(np.float32)
+        ut.backward(torch.from_numpy(duv).to(dev))
+        assert np.array_equal(xt.grad.cpu().numpy().reshape(B2, C2, -1), onp.dark_regroup_bwd(duv, B2, C2, g2))
+    with pytest.raises(RuntimeError):
+        capsb.dark_regroup(torch.zeros(2, 12, 28, 28, device=dev), 7)        # Cch not a multiple of 8
+    with pytest.raises(RuntimeError):
+        capsb.dark_regroup(torch.zeros(2, 16, 28, 28), 7)                     # CPU tensor

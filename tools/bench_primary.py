@@ -23,6 +23,13 @@ def reference_formulation(x, convs):
     return (sq / (1 + sq)) * v / torch.sqrt(sq)
 
 
+def reference_regroup(x, g):
+    B = x.size(0)
+    xs = torch.chunk(x.view(B, 256, 4, 4 * g ** 2), g ** 2, 3)                                   # reference models.py:395
+    xs = [xx.permute(0, 2, 3, 1).contiguous().view(B, -1, 8).unsqueeze(0) for xx in xs]          # :397
+    return torch.cat(xs, 0).view(-1, 512, 8)                                                     # :398, :400
+
+
 def timed(fn, x, gu, steps):
     for _ in range(3):
         x.grad = None
@@ -60,12 +67,28 @@ def main():
         x.grad = None
         u = layer(x)
         u.backward(gu)
-        du_rel = float((u - u_ref).abs().max() / u_ref.abs().max())
+        du_rel = float((u.detach() - u_ref.detach()).abs().max() / u_ref.detach().abs().max())
         dx_rel = float((x.grad - dx_ref).abs().max() / dx_ref.abs().max())
         t_ref = timed(lambda t: reference_formulation(t, layer.capsules), x, gu, args.steps)
         t_new = timed(layer, x, gu, args.steps)
         print('| %d | %.3f | %.3f | %.2fx | %.1e | %.1e |' % (B, t_ref, t_new, t_ref / t_new, du_rel, dx_rel))
 
 
+def dark():
+    dev = torch.device('cuda')
+    print()
+    print('DarkCapsuleNet cell regroup (reference models.py:393-399), x [B,256,28,28] -> u [49 B,512,8], fwd + bwd')
+    print('| B | reference formulation (view, chunk, 49 x permute/contiguous/view, cat) ms | caps_dark_regroup ms | speed-up | identical |')
+    print('|---|---|---|---|---|')
+    for B in (32, 256):
+        x = torch.randn(B, 256, 28, 28, device=dev, requires_grad=True)
+        gu = torch.randn(49 * B, 512, 8, device=dev)
+        same = bool(torch.equal(reference_regroup(x, 7), capsb.dark_regroup(x, 7)))
+        t_ref = timed(lambda t: reference_regroup(t, 7), x, gu, 10)
+        t_new = timed(lambda t: capsb.dark_regroup(t, 7), x, gu, 10)
+        print('| %d | %.3f | %.3f | %.1fx | %s |' % (B, t_ref, t_new, t_ref / t_new, same))
+
+
 if __name__ == '__main__':
     main()
+    dark()
