@@ -28,6 +28,7 @@ SYMBOLS = {
     'caps_primary_squash_backward': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'caps_dark_regroup': (_i, [_vp, _vp, _i, _i, _i, _vp]),
     'caps_dark_regroup_backward': (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    'caps_dark_loss': (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'caps_route_step_host_scratch_bytes': (_sz, [_i] * 6),
     'caps_route_step_host': (_i, [_vp] * 8 + [_sz] + [_i] * 6 + [_vp]),
     'caps_set_tuning': (_i, [ctypes.c_char_p, _i]),

@@ -244,6 +244,42 @@ def dark_regroup(x, n_grid):
     return _DarkRegroupFn.apply(x, G)
 
 
+class _DarkLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, y):
+        L = _cabi.lib()
+        B, G, Y = y.shape[0], y.shape[1] * y.shape[2], y.shape[3]
+        v2 = v.reshape(G * B, 5).contiguous()
+        y = y.to(device=v.device, dtype=torch.float32).contiguous()
+        loss = torch.empty((), device=v.device, dtype=torch.float32)
+        grad = torch.empty_like(v2) if ctx.needs_input_grad[0] else None
+        scratch = torch.empty((_cabi.MARGIN_SCRATCH_FLOATS,), device=v.device, dtype=torch.float32)
+        with torch.cuda.device(v.device):
+            _cabi.check(L.caps_dark_loss(_ptr(v2), _ptr(y), 1.0 / B, _ptr(loss), _ptr(grad), _ptr(scratch), B, G, Y, _stream()),
+                        'caps_dark_loss')
+        ctx.save_for_backward(grad)
+        ctx.vshape = v.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (grad,) = ctx.saved_tensors
+        return (grad * gl).reshape(ctx.vshape), None
+
+
+def dark_capsule_loss(v, y):
+    """Reference `darkcapsule_loss(caps, y, params)` (loss_fns.py:187-204, recon off) taken directly on
+    the routing layer's output: v [g*g*B, ..., 5] (any shape with g*g*B*5 elements in the routing
+    batch order q*B + b, e.g. the layer's [g*g*B,1,1,1,5]) and the label tensor y [B,g,g,>=5].
+    Loss value and its gradient w.r.t. v come out of one kernel."""
+    if not v.is_cuda or v.dtype != torch.float32:
+        raise RuntimeError('dark_capsule_loss runs on CUDA fp32 tensors only')
+    if y.dim() != 4 or y.shape[3] < 5 or v.numel() != y.shape[0] * y.shape[1] * y.shape[2] * 5:
+        raise RuntimeError('dark_capsule_loss: expected v with B*g*g*5 elements and y [B,g,g,>=5], got %s and %s'
+                           % (tuple(v.shape), tuple(y.shape)))
+    return _DarkLossFn.apply(v, y)
+
+
 def dynamic_routing(u, route_weights, n_iter=3, return_couplings=False):
     """u [B,N,K], route_weights [1,N,C,K,D]  ->  v [B,C,D] (and the last couplings c [B,N,C])."""
     return _RoutingFn.apply(u, route_weights, int(n_iter), bool(return_couplings))

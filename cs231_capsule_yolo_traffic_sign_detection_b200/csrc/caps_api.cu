@@ -497,6 +497,21 @@ int caps_dark_regroup_backward(const float* du, float* dx, int B, int Cch, int G
     return 0;
 }
 
+int caps_dark_loss(const float* v, const float* y, float scale, float* loss, float* grad_v, float* scratch,
+                   int B, int G, int Y, void* stream) {
+    if (!v || !y || !loss || B < 0 || G <= 0 || Y < 5) return fail(CAPS_E_BADARG, "caps_dark_loss: bad argument (Y >= 5)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long n = (long)B * G;
+    const int blocks = scratch ? (int)std::min<long>(std::max<long>(cdiv(n, 256), 1), CAPS_MARGIN_SCRATCH_FLOATS) : 1;
+    { LaunchScope ls_(kcLoss, st); k_dark_loss<<<blocks, 256, 0, st>>>(v, y, scale, loss, scratch, grad_v, B, G, Y); }
+    LAUNCH_CHECK();
+    if (blocks > 1) {
+        { LaunchScope ls_(kcLoss, st); k_margin_loss_final<<<1, 256, 0, st>>>(scratch, blocks, scale, loss); }
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 // ---- host-buffer step ------------------------------------------------------------------------
 // The batch is cut into up to three micro-batches (B/8, 3B/8, B/2, multiples of 128) so that the
 // host->device copy of micro-batch m+1 (on an internal copy stream) runs under the kernels of

@@ -793,6 +793,57 @@ static __global__ void k_margin_loss_final(const float* __restrict__ part, int n
     if (threadIdx.x == 0) *loss = red[0] * scale;
 }
 
+// ---------------------------------------------------------------------------------------------
+// DarkCapsuleNet loss tail (reference loss_fns.py:187-204 with utils.polar_transform, utils.py:69-85; recon off):
+//   v [G*B][5] is the routing layer's output, row q*B + b = cell q of sample b (what models.py:400 produces before its
+//   view(g,g,B,5).permute(2,0,1,3)); y [B][G][Y] holds (r, x, y, w, h, classes...) per cell.
+//   loss = scale * sum_cells [ y_r relu(0.9 - |v|)^2 + 0.5 (1 - y_r) relu(|v| - 0.1)^2 - v . y_phi ]
+//   grad_v (nullable) = d loss / d v in v's own layout, ready to be caps_route_backward's grad_v.
+// Fixed-order two-level reduction like k_margin_loss (k_margin_loss_final adds the partials).
+// ---------------------------------------------------------------------------------------------
+static __global__ void k_dark_loss(const float* __restrict__ v, const float* __restrict__ y, float scale,
+                                   float* __restrict__ loss, float* __restrict__ part, float* __restrict__ grad_v,
+                                   int B, int G, int Y) {
+    __shared__ float red[256];
+    float acc = 0.f;
+    const long n = (long)B * G;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(e / B);
+        const long b = e % B;                                   // e = q*B + b: v's row
+        const float* p = v + e * 5;
+        const float* t = y + ((size_t)b * G + q) * Y;
+        const float pi = 3.14159265358979323846f;
+        const float yr = t[0];
+        float s1, c1, s2, c2, s3, c3, s4, c4;
+        sincosf(t[1] * pi, &s1, &c1);                           // f1 = x pi, f2 = y pi, f3 = h pi, f4 = w 2 pi (utils.py:74)
+        sincosf(t[2] * pi, &s2, &c2);
+        sincosf(t[4] * pi, &s3, &c3);
+        sincosf(t[3] * pi * 2.f, &s4, &c4);
+        const float phi[5] = {s1, s1 * c2, s1 * s2 * c3, s1 * s2 * s3 * c4, s1 * s2 * s3 * s4};
+        float m2 = 0.f, dot = 0.f;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) { m2 = fmaf(p[d], p[d], m2); dot = fmaf(p[d], phi[d], dot); }
+        const float m = sqrtf(m2);
+        const float l = fmaxf(0.9f - m, 0.f), r = fmaxf(m - 0.1f, 0.f);
+        acc += yr * l * l + 0.5f * (1.f - yr) * r * r - dot;
+        if (grad_v != nullptr) {
+            const float dm = (-2.f * yr * l + (1.f - yr) * r) / m;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) grad_v[e * 5 + d] = scale * (dm * p[d] - phi[d]);
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (gridDim.x == 1) *loss = red[0] * scale;
+        else part[blockIdx.x] = red[0];
+    }
+}
+
 static __global__ void k_squash_rows(const float* __restrict__ x, float* __restrict__ y, long rows, int D) {
     const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;

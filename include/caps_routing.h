@@ -114,6 +114,19 @@ int caps_primary_squash_backward(const float* conv, const float* du, float* dcon
 int caps_dark_regroup(const float* x, float* u, int B, int Cch, int G, void* stream);
 int caps_dark_regroup_backward(const float* du, float* dx, int B, int Cch, int G, void* stream);
 
+/* DarkCapsuleNet loss tail, the step directly after the routing layer in that model (SURVEY.md
+ * section 8(f) row 3; reference loss_fns.py:187-204 `darkcapsule_loss` with `utils.polar_transform`,
+ * utils.py:69-85; reconstruction term off).  v [G*B][5]: the routing layer's output, row q*B + b =
+ * cell q of sample b (what models.py:400 returns before its view/permute); y [B][G][Y], Y >= 5, the
+ * label tensor's (r, x, y, w, h) in columns 0..4.
+ *   loss = scale * sum over cells of  y_r relu(0.9-|v|)^2 + 0.5 (1-y_r) relu(|v|-0.1)^2 - v . y_phi
+ * (scale = 1/B is the reference's `/ y.size(0)`).  grad_v (nullable) [G*B][5] = d loss / d v, in the
+ * layout caps_route_backward takes as grad_v.  scratch: CAPS_MARGIN_SCRATCH_FLOATS floats or NULL
+ * (single block).  One kernel for the norm, both relu branches, the four sin/cos pairs, the
+ * products, the sum -- and the gradient autograd would need ~25 more launches for. */
+int caps_dark_loss(const float* v, const float* y, float scale, float* loss, float* grad_v,
+                   float* scratch, int B, int G, int Y, void* stream);
+
 /* HOST-buffer step, the end-to-end call: copies u (and y) host->device, runs forward, margin
  * loss, fused backward, and copies loss (and, if non-NULL, v / du / dW) device->host, all on
  * `stream`, then synchronises that stream.  u_host/y_host/..._host are HOST pointers (pinned for

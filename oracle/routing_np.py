@@ -11,6 +11,7 @@ of the caps->caps branch of the reference `CapsuleLayer`:
     reference models.py:70-79   prediction vectors + routing loop
     reference models.py:81-82   primary-capsule tail (views + cat + squash), the step before the routing layer
     reference models.py:393-399 DarkCapsuleNet cell regroup, the step before the routing layer in that model
+    reference loss_fns.py:187-204, utils.py:69-85  darkcapsule_loss + polar_transform, the step after it
     reference models.py:116-117 class scores (norm of the class capsules)
     reference loss_fns.py:11-17,23  margin loss (recon term excluded: it is not on the path)
 
@@ -69,6 +70,25 @@ def dark_regroup_bwd(du, B, Cch, n_grid):
     G = n_grid * n_grid
     dv = du.reshape(G, B, 4, 4, Cch)                       # [q, b, a, t, ch]
     return np.ascontiguousarray(dv.transpose(1, 4, 2, 0, 3)).reshape(B, Cch, 16 * G)      # [b, ch, a, q, t]
+
+
+def polar_transform(x):
+    """reference utils.py:69-85 -- (r, x, y, w, h) -> r and the 5-d direction vector."""
+    r, xx, yy, w, h = [x[..., k] for k in range(5)]
+    f1, f2, f3, f4 = xx * np.pi, yy * np.pi, h * np.pi, w * np.pi * 2
+    s1, c1, s2, c2, s3, c3, s4, c4 = np.sin(f1), np.cos(f1), np.sin(f2), np.cos(f2), np.sin(f3), np.cos(f3), np.sin(f4), np.cos(f4)
+    return r, np.stack([s1, s1 * c2, s1 * s2 * c3, s1 * s2 * s3 * c4, s1 * s2 * s3 * s4], axis=-1)
+
+
+def dark_loss(caps, y):
+    """reference loss_fns.py:187-204 (recon off): caps [B,g,g,5], y [B,g,g,>=5] -> (loss, d loss / d caps)."""
+    y_r, y_phi = polar_transform(y[..., :5])
+    m = np.sqrt((caps * caps).sum(-1))
+    left, right = np.maximum(0.9 - m, 0.0), np.maximum(m - 0.1, 0.0)
+    B = y.shape[0]
+    loss = ((y_r * left ** 2 + 0.5 * (1 - y_r) * right ** 2).sum() - (caps * y_phi).sum()) / B
+    dm = (-2.0 * y_r * left + (1 - y_r) * right) / m
+    return loss, (dm[..., None] * caps - y_phi) / B
 
 
 def softmax_c(b):

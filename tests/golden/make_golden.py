@@ -165,6 +165,23 @@ def make_dark_regroup(ref_models):
                                                 os.path.getsize(path) // 1024))
 
 
+def make_dark_loss(ref_loss):
+    """reference darkcapsule_loss (loss_fns.py:187-204, recon off) + autograd on seeded caps / labels."""
+    B, g = 4, 7
+    gen = torch.Generator().manual_seed(41)
+    caps = (0.6 * torch.randn(B, g, g, 5, generator=gen)).requires_grad_(True)
+    y = torch.zeros(B, g, g, 48)
+    y[..., 0] = (torch.rand(B, g, g, generator=gen) < 0.15).float()
+    y[..., 1:5] = 0.05 + 0.9 * torch.rand(B, g, g, 4, generator=gen)
+    loss = ref_loss.darkcapsule_loss(caps, y, P())
+    loss.backward()
+    path = os.path.join(HERE, 'dark_loss.npz')
+    np.savez_compressed(path, caps=caps.detach().numpy(), y5=y[..., :5].numpy(), loss=np.float32(loss.item()),
+                        dcaps=caps.grad.numpy())
+    print('%-20s caps %s loss %.6f -> %s (%d KB)' % ('dark_loss', tuple(caps.shape), loss.item(), os.path.basename(path),
+                                                     os.path.getsize(path) // 1024))
+
+
 def main():
     from oracle import routing_np as onp
     ref_models, ref_loss = import_reference()
@@ -172,6 +189,7 @@ def main():
     torch.set_num_threads(1)   # one thread: reduction order (hence the fp32 bits) is reproducible
     make_primary(ref_models)
     make_dark_regroup(ref_models)
+    make_dark_loss(ref_loss)
     if '--primary-only' in sys.argv:
         return
     for name, (B, N, C, K, D, R, seed, full) in CASES.items():

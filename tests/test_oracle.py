@@ -142,3 +142,17 @@ def test_dark_regroup_matches_reference():
     du = dark_pattern(u.shape, 104729, 8179)
     dx = onp.dark_regroup_bwd(du, B, Cch, grid)
     assert np.array_equal(dx.reshape(x.shape), g['dx'].astype(np.float32))
+
+
+def test_dark_loss_matches_reference():
+    """darkcapsule_loss + polar_transform (reference loss_fns.py:187-204, utils.py:69-85) and the gradient
+    autograd gives for it (tests/golden/dark_loss.npz)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import routing_np as onp
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'dark_loss.npz')))
+    y = np.zeros(g['y5'].shape[:3] + (48,))
+    y[..., :5] = g['y5']
+    loss, dcaps = onp.dark_loss(g['caps'].astype(np.float64), y)
+    assert abs(loss - float(g['loss'])) < 1e-6 * abs(float(g['loss']))
+    assert rel_err(dcaps, g['dcaps']) < 1e-6

@@ -401,3 +401,72 @@ def test_dark_regroup_kernel(capsb):
         capsb.dark_regroup(torch.zeros(2, 12, 28, 28, device=dev), 7)        # Cch not a multiple of 8
     with pytest.raises(RuntimeError):
         capsb.dark_regroup(torch.zeros(2, 16, 28, 28), 7)                     # CPU tensor
+
+
+def _rows_from_caps(caps):
+    """[B,g,g,5] -> the routing layer's row order [g*g*B, 5] (row q*B + b), inverse of models.py:401"""
+    B, g = caps.shape[0], caps.shape[1]
+    return np.ascontiguousarray(caps.transpose(1, 2, 0, 3)).reshape(g * g * B, 5)
+
+
+def test_dark_loss_kernel(capsb):
+    """caps_dark_loss (value + gradient in one kernel) against the reference's darkcapsule_loss and autograd."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import routing_np as onp
+    dev = torch.device('cuda')
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'dark_loss.npz')))
+    B, grid = g['caps'].shape[0], g['caps'].shape[1]
+    y = np.zeros((B, grid, grid, 48), dtype=np.float32)
+    y[..., :5] = g['y5']
+    v = torch.from_numpy(_rows_from_caps(g['caps'])).to(dev).view(grid * grid * B, 1, 1, 1, 5).requires_grad_(True)
+    loss = capsb.dark_capsule_loss(v, torch.from_numpy(y).to(dev))
+    assert abs(float(loss) - float(g['loss'])) < 2e-6 * abs(float(g['loss']))
+    (3.0 * loss).backward()
+    assert rel_err(v.grad.cpu().numpy().reshape(-1, 5), 3.0 * _rows_from_caps(g['dcaps'])) < 1e-5
+    # a batch large enough for the two-level reduction, against the oracle
+    rng = np.random.default_rng(8)
+    B2, g2 = 300, 7
+    caps = (0.5 * rng.standard_normal((B2, g2, g2, 5))).astype(np.float32)
+    y2 = rng.uniform(0.05, 0.95, (B2, g2, g2, 6)).astype(np.float32)
+    y2[..., 0] = (rng.uniform(size=(B2, g2, g2)) < 0.1)
+    v2 = torch.from_numpy(_rows_from_caps(caps)).to(dev).requires_grad_(True)
+    l2 = capsb.dark_capsule_loss(v2, torch.from_numpy(y2).to(dev))
+    l2.backward()
+    lo, go = onp.dark_loss(caps.astype(np.float64), y2.astype(np.float64))
+    assert abs(float(l2) - lo) < 1e-5 * abs(lo)
+    assert rel_err(v2.grad.cpu().numpy(), _rows_from_caps(go)) < 1e-5
+
+
+def test_dark_capsule_chain(capsb):
+    """regroup -> routing (512 -> 1 x 5, the DarkCapsuleNet head) -> darkcapsule loss, forward and backward,
+    against the same chain assembled from the oracle's pieces."""
+    from oracle import routing_np as onp
+    dev = torch.device('cuda')
+    rng = np.random.default_rng(12)
+    B, grid, R = 3, 2, 3
+    G = grid * grid
+    x = (0.3 * rng.standard_normal((B, 256, 4 * grid, 4 * grid))).astype(np.float32)
+    W = (0.1 * rng.standard_normal((512, 1, 8, 5))).astype(np.float32)
+    y = rng.uniform(0.05, 0.95, (B, grid, grid, 48)).astype(np.float32)
+    y[..., 0] = (rng.uniform(size=(B, grid, grid)) < 0.3)
+    # oracle chain (fp64)
+    u = onp.dark_regroup(x.astype(np.float64), grid)
+    v, state = onp.routing_forward(u, W.astype(np.float64), R, return_state=True)        # [G*B,1,5]
+    caps = v.reshape(grid, grid, B, 5).transpose(2, 0, 1, 3)                              # models.py:401
+    loss, dcaps = onp.dark_loss(caps, y.astype(np.float64))
+    gv = np.ascontiguousarray(dcaps.transpose(1, 2, 0, 3)).reshape(G * B, 1, 5)
+    du, dW = onp.routing_backward(u, W.astype(np.float64), gv, R, state=state)
+    dx = onp.dark_regroup_bwd(du, B, 256, grid).reshape(x.shape)
+    # device chain
+    layer = capsb.CapsuleLayer(None, n_caps=1, n_nodes=512, in_C=8, out_C=5, n_iter=R).to(dev)
+    with torch.no_grad():
+        layer.route_weights.copy_(torch.from_numpy(W)[None])
+    xt = torch.from_numpy(x).to(dev).requires_grad_(True)
+    out = layer(capsb.dark_regroup(xt, grid))                                             # [G*B,1,1,1,5]
+    lt = capsb.dark_capsule_loss(out, torch.from_numpy(y).to(dev))
+    lt.backward()
+    assert abs(float(lt) - loss) < 1e-5 * max(abs(loss), 1.0)       # margin and coordinate terms cancel here: the sum is ~0.005
+    assert rel_err(out.detach().cpu().numpy().reshape(G * B, 1, 5), v) < TOL_V
+    assert rel_err(xt.grad.cpu().numpy(), dx) < TOL_G
+    assert rel_err(layer.route_weights.grad[0].cpu().numpy(), dW) < TOL_G
