@@ -313,13 +313,14 @@ template <int NISS, int NPROD, int EXTRA, int PAIR = 0>   // PAIR: epilogue wait
 __global__ void __launch_bounds__(384, 1) k_full(int reps, long long* cycles, float* sink, const float* src, float* outbuf) {
     extern __shared__ __align__(1024) uint8_t dsm[];
     constexpr int NS = 10, SB = (EXTRA == 1) ? 20480 : 16384;
-    __shared__ __align__(8) uint64_t bars[8 + 2 * NS];
+    __shared__ __align__(8) uint64_t bars[12 + 2 * NS];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stages = smem_u32(dsm);
     const uint32_t full = smem_u32(&bars[0]), empty = smem_u32(&bars[4]), sfull = smem_u32(&bars[8]), sempty = smem_u32(&bars[8 + NS]);
+    const uint32_t full2 = smem_u32(&bars[8 + 2 * NS]);      // SPLIT: second column half
     if (tid == 0) {
-        for (int t = 0; t < 4; ++t) { mbar_init(full + 8 * t, 1); mbar_init(empty + 8 * t, 8); }
+        for (int t = 0; t < 4; ++t) { mbar_init(full + 8 * t, 1); mbar_init(full2 + 8 * t, 1); mbar_init(empty + 8 * t, 8); }
         for (int q = 0; q < NS; ++q) { mbar_init(sfull + 8 * q, 1); mbar_init(sempty + 8 * q, EXTRA == 1 ? 9 : 1); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -355,6 +356,11 @@ __global__ void __launch_bounds__(384, 1) k_full(int reps, long long* cycles, fl
             { long spins = 0; while (!mbar_try(sfull + 8 * q, (n / NS) & 1)) if (++spins > (1L << 22)) __trap(); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t a_hi = d0 + (uint64_t)((q * SB) >> 4), a_lo = a_hi + (4096 >> 4), b_hi = a_hi + (8192 >> 4), b_lo = b_hi + (4096 >> 4);
+            if (PAIR == 2) {
+                constexpr uint32_t idesc64 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                stage_mma(tmem_base + t * 128, a_hi, a_lo, b_hi, b_lo, idesc64, full + 8 * t);
+                stage_mma(tmem_base + t * 128 + 64, a_hi, a_lo, b_hi + (1024 >> 4), b_lo + (1024 >> 4), idesc64, full2 + 8 * t);
+            } else
             stage_mma(tmem_base + t * 128, a_hi, a_lo, b_hi, b_lo, idesc, full + 8 * t);
             asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
                          "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(sempty + 8 * q) : "memory");
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(384, 1) k_full(int reps, long long* cycles, fl
         const long long t0 = clock64();
         for (int n = 0; n < reps; ++n) {
             const int t = n & 3, q = n % NS;
-            if (PAIR && !(n & 1) && n + 1 < reps) {
+            if (PAIR == 1 && !(n & 1) && n + 1 < reps) {
                 // both stages' barriers probed in one go: the second round trip hides under the first
                 uint32_t ok0, ok1;
                 asm volatile("{\n\t.reg .pred p0, p1;\n\t"
@@ -380,6 +386,9 @@ __global__ void __launch_bounds__(384, 1) k_full(int reps, long long* cycles, fl
                              : "r"(full + 8 * t), "r"((n >> 2) & 1), "r"(full + 8 * ((n + 1) & 3)), "r"(((n + 1) >> 2) & 1) : "memory");
                 if (!ok0) { long spins = 0; while (!mbar_try(full + 8 * t, (n >> 2) & 1)) if (++spins > (1L << 22)) __trap(); }
                 if (!ok1) { long spins = 0; while (!mbar_try(full + 8 * ((n + 1) & 3), ((n + 1) >> 2) & 1)) if (++spins > (1L << 22)) __trap(); }
+            } else if (PAIR == 2) {
+                const uint32_t fb = (jh ? full2 : full) + 8 * t;
+                long spins = 0; while (!mbar_try(fb, (n >> 2) & 1)) if (++spins > (1L << 22)) __trap();
             } else if (!PAIR || n + 1 >= reps) {
                 long spins = 0; while (!mbar_try(full + 8 * t, (n >> 2) & 1)) if (++spins > (1L << 22)) __trap();
             }
@@ -507,6 +516,10 @@ int main() {
         run_full<2, 2, 0, 1>(reps, dc, sink, src, outbuf);
         run_full<2, 2, 1, 1>(reps, dc, sink, src, outbuf);
         run_full<2, 2, 2, 1>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 0, 2>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 1, 2>(reps, dc, sink, src, outbuf);
+        run_full<2, 2, 2, 2>(reps, dc, sink, src, outbuf);
+        run_full<1, 1, 1, 2>(reps, dc, sink, src, outbuf);
         run_full<2, 2, 3>(reps, dc, sink, src, outbuf);
         run_full<2, 2, 4>(reps, dc, sink, src, outbuf);
         run_full<2, 2, 5>(reps, dc, sink, src, outbuf);
