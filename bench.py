@@ -307,8 +307,8 @@ def main_gpu(args, rank, world, device):
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))
         if tj.get('batch') == B and tj.get('n_nodes') == N:
-            key = 'k_grad_mma<5>' if dom.startswith('k_grad') else 'k_pass_tc<1>'
-            traffic = tj['kernels'][key]['dram_bytes_per_launch']
+            pref = 'k_grad_mma<5' if dom.startswith('k_grad') else 'k_pass_tc<1>'
+            traffic = [v['dram_bytes_per_launch'] for k, v in tj['kernels'].items() if k.startswith(pref)][0]
     except Exception:
         pass
     roofline = {'bound': 'hbm', 'kernel': '%s; %d launches/step' % (dom, dom_n // args.steps),
