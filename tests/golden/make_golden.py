@@ -182,6 +182,36 @@ def make_dark_loss(ref_loss):
                                                      os.path.getsize(path) // 1024))
 
 
+def make_capsnet(ref_models, ref_loss):
+    """configs[0] shape: the reference's full CapsuleNet (conv1 -> primary capsules -> routing -> scores), capsule_loss
+    (recon off) and autograd, batch 4, seeded construction (torch.manual_seed(0): the drop-in layers draw the same
+    weights, tests/test_cabi_cpu.py) -- so the fixture only stores outputs and strided gradient probes."""
+    B = 4
+    params = P()
+    params.n_classes = 43
+    torch.manual_seed(0)
+    model = ref_models.CapsuleNet(params)
+    gen = torch.Generator().manual_seed(51)
+    x = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1                 # U[-1,1) like utils.center_rgb
+    y = torch.randint(0, 43, (B,), generator=gen)
+    x.requires_grad_(True)
+    scores = model(x)
+    loss = ref_loss.capsule_loss(scores, y, params)
+    loss.backward()
+    pw = torch.cat([m.weight.grad.reshape(-1) for m in model.primary_capsules.capsules])
+    pb = torch.cat([m.bias.grad.reshape(-1) for m in model.primary_capsules.capsules])
+    st = 97
+    path = os.path.join(HERE, 'capsnet_cfg1.npz')
+    np.savez_compressed(path, dims=np.array([B, 51, st], dtype=np.int64), y=y.numpy(), scores=scores.detach().numpy(),
+                        loss=np.float32(loss.item()), dx=x.grad.numpy(),
+                        conv1_w_probe=model.conv1.weight.grad.reshape(-1)[::st].numpy().copy(),
+                        conv1_b=model.conv1.bias.grad.numpy(), prim_w_probe=pw[::st].numpy().copy(), prim_b=pb.numpy(),
+                        route_w_probe=model.traffic_sign_capsules.route_weights.grad.reshape(-1)[::st * 11].numpy().copy(),
+                        x_checksum=np.float64(x.detach().double().sum().item()))
+    print('%-20s scores %s loss %.6f -> %s (%d KB)' % ('capsnet_cfg1', tuple(scores.shape), loss.item(), os.path.basename(path),
+                                                     os.path.getsize(path) // 1024))
+
+
 def main():
     from oracle import routing_np as onp
     ref_models, ref_loss = import_reference()
@@ -190,6 +220,7 @@ def main():
     make_primary(ref_models)
     make_dark_regroup(ref_models)
     make_dark_loss(ref_loss)
+    make_capsnet(ref_models, ref_loss)
     if '--primary-only' in sys.argv:
         return
     for name, (B, N, C, K, D, R, seed, full) in CASES.items():

@@ -470,3 +470,43 @@ def test_dark_capsule_chain(capsb):
     assert rel_err(out.detach().cpu().numpy().reshape(G * B, 1, 5), v) < TOL_V
     assert rel_err(xt.grad.cpu().numpy(), dx) < TOL_G
     assert rel_err(layer.route_weights.grad[0].cpu().numpy(), dW) < TOL_G
+
+
+def test_capsnet_cfg1_end_to_end(capsb):
+    """BASELINE.json configs[0] shape: the reference's CapsuleNet (conv1 -> primary capsules -> routing -> scores,
+    reference models.py:86-117) + capsule_loss + backward, rebuilt here from the drop-in layers in the reference's
+    construction order under the same seed (the drop-in draws the same weights: tests/test_cabi_cpu.py), against
+    what the unmodified reference produced on the CPU (tests/golden/capsnet_cfg1.npz)."""
+    import os
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from conftest import GOLDEN_DIR
+    dev = torch.device('cuda')
+    g = dict(np.load(os.path.join(GOLDEN_DIR, 'capsnet_cfg1.npz')))
+    B, xseed, st = [int(v) for v in g['dims']]
+    torch.manual_seed(0)
+    conv1 = nn.Conv2d(3, 256, 9)                                                     # models.py:90
+    primary = capsb.CapsuleLayer(None, n_caps=8, n_nodes=-1, in_C=256, out_C=16, kernel=8, stride=2)
+    digits = capsb.CapsuleLayer(None, n_caps=43, n_nodes=16 * 9 * 9, in_C=8, out_C=16)
+    gen = torch.Generator().manual_seed(xseed)
+    x = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1
+    y = torch.randint(0, 43, (B,), generator=gen)
+    assert abs(float(x.double().sum()) - float(g['x_checksum'])) < 1e-9 and np.array_equal(y.numpy(), g['y'])
+    conv1, primary, digits = conv1.to(dev), primary.to(dev), digits.to(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    xd = x.to(dev).requires_grad_(True)
+    u = primary(F.relu(conv1(xd)))                                                   # models.py:113-114
+    out, loss = digits.forward_margin_loss(u, y.to(dev))                             # models.py:115-117 + loss_fns.py:11-23
+    scores = (out.squeeze() ** 2).sum(dim=-1) ** 0.5
+    assert rel_err(scores.detach().cpu().numpy(), g['scores']) < 2e-5
+    assert abs(float(loss) - float(g['loss'])) < 2e-5 * abs(float(g['loss']))
+    loss.backward()
+    tol = 2e-4
+    assert rel_err(xd.grad.cpu().numpy(), g['dx']) < tol
+    assert rel_err(conv1.weight.grad.reshape(-1)[::st].cpu().numpy(), g['conv1_w_probe']) < tol
+    assert rel_err(conv1.bias.grad.cpu().numpy(), g['conv1_b']) < tol
+    pw = torch.cat([m.weight.grad.reshape(-1) for m in primary.capsules])
+    pb = torch.cat([m.bias.grad.reshape(-1) for m in primary.capsules])
+    assert rel_err(pw[::st].cpu().numpy(), g['prim_w_probe']) < tol
+    assert rel_err(pb.cpu().numpy(), g['prim_b']) < tol
+    assert rel_err(digits.route_weights.grad.reshape(-1)[::st * 11].cpu().numpy(), g['route_w_probe']) < tol
