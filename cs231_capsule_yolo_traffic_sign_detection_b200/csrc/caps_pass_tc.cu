@@ -190,22 +190,23 @@ __global__ void k_prep_u_tc(const float* __restrict__ u, float* __restrict__ ua,
     }
 }
 
-// W [N][C][8][16] -> wb [N][JG][hi/lo][kq][128 rows][4]  (row n = 16*(j - 8*jg) + d; 4 = k % 4)
-__global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb, int N, int C, int JG) {
+// W [N][C][8][D] -> wb [N][JG][hi/lo][kq][128 rows][4]  (D = 16 or 32, 128/D capsules per group;
+// row n = D*(j - (128/D)*jg) + d; 4 = k % 4)
+__global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb, int N, int C, int JG, int D) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * JG * 128) return;
     const int n = (int)(idx & 127);
     const long ig = idx >> 7;
     const int jg = (int)(ig % JG);
     const long i = ig / JG;
-    const int j = jg * kTcJW + (n >> 4), d = n & 15;
+    const int j = jg * (128 / D) + n / D, d = n % D;
     float* dst = wb + (size_t)ig * 2048 + n * 4;
 #pragma unroll
     for (int kq = 0; kq < 2; ++kq) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
         if (j < C) {
-            const float* src = W + (((size_t)i * C + j) * 8 + kq * 4) * 16 + d;
-            x = make_float4(__ldg(src), __ldg(src + 16), __ldg(src + 32), __ldg(src + 48));
+            const float* src = W + (((size_t)i * C + j) * 8 + kq * 4) * D + d;
+            x = make_float4(__ldg(src), __ldg(src + D), __ldg(src + 2 * D), __ldg(src + 3 * D));
         }
         split4(x, hi, lo);
         st4(dst + (0 * 2 + kq) * 512, hi);
@@ -226,8 +227,11 @@ struct PassTcParams {
     int dbg;             // TIMING EXPERIMENTS ONLY (tuning knob "tcdbg"): 1 = skip the L-mode stores, 2 = skip the coefficient copies
 };
 
-template <int MODE>
+// DD = class-capsule dimension: 16 (8 capsules per CTA, 4 per epilogue warp) or 32 (4 per CTA, 2 per warp); the MMA
+// tile, the TMEM layout and the 64 accumulator columns per epilogue warp are the same for both.
+template <int MODE, int DD>
 __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
+    constexpr int JW = 128 / DD;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int ns = p.ns;
     constexpr int kTcStageBytes = tc_stage_bytes(MODE);
@@ -273,10 +277,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
         int s = w;
         uint32_t ph = 1;                                 // parity to wait for on smem_empty (first lap passes)
         // kModeA: + one copy per valid lane tile of the quad: coef[tile][i][8 jg .. +nj][32] (nj * 128 bytes)
-        const int nj = min(kTcJW, p.C - jg * kTcJW);
+        const int nj = min(JW, p.C - jg * JW);
         const uint32_t cbytes = (uint32_t)nj * 128u;
         const size_t ctile = (size_t)p.N * p.C * kLanes;                 // coef elements per lane tile
-        const float* csrc = MODE == kModeA ? p.coef + ((size_t)(tq * 4) * p.N + i_begin + w) * p.C * kLanes + (size_t)jg * kTcJW * kLanes : nullptr;
+        const float* csrc = MODE == kModeA ? p.coef + ((size_t)(tq * 4) * p.N + i_begin + w) * p.C * kLanes + (size_t)jg * JW * kLanes : nullptr;
         const size_t cstep = (size_t)p.C * kLanes * NI;
         const int nvt = (p.dbg & 2) ? 0 : min(4, p.nbt - tq * 4);        // valid lane tiles in this quad (>= 1)
         const uint32_t txbytes = (uint32_t)kTcOperandBytes + (MODE == kModeA ? (uint32_t)nvt * cbytes : 0u);
@@ -362,30 +366,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
         }
     } else {
         // ===== epilogue: warp w -> samples of lane tile 4*tq + w%4, capsules j0 .. j0+JPW-1 =====
-        constexpr int JPW = kTcJPW, NC = 16 * JPW;
+        constexpr int JPW = JW / (kTcEpiWarps / 4), NC = DD * JPW, D4 = DD / 4;
+        static_assert(NC == 64, "64 accumulator columns per epilogue warp");
         const int q = warp & 3, jh = warp >> 2;
         const int tile = tq * 4 + q;
         const bool tvalid = tile < p.nbt;
-        const int j0 = jg * kTcJW + jh * JPW;
-        float acc[JPW][16];                 // A modes: running sums; L mode: the probe vectors X[b,j,:]
+        const int j0 = jg * JW + jh * JPW;
+        float acc[JPW][DD];                 // A modes: running sums; L mode: the probe vectors X[b,j,:]
 #pragma unroll
         for (int jj = 0; jj < JPW; ++jj)
 #pragma unroll
-            for (int d = 0; d < 16; ++d) acc[jj][d] = 0.f;
+            for (int d = 0; d < DD; ++d) acc[jj][d] = 0.f;
         if (MODE == kModeL && tvalid) {
 #pragma unroll
             for (int jj = 0; jj < JPW; ++jj)
                 if (j0 + jj < p.C) {
 #pragma unroll
-                    for (int dq = 0; dq < 4; ++dq) {
-                        const float4 x = ldg4(p.X + ((((size_t)tile * p.C + j0 + jj) * 4 + dq) * kLanes + lane) * 4);
+                    for (int dq = 0; dq < D4; ++dq) {
+                        const float4 x = ldg4(p.X + ((((size_t)tile * p.C + j0 + jj) * D4 + dq) * kLanes + lane) * 4);
                         acc[jj][dq * 4 + 0] = x.x; acc[jj][dq * 4 + 1] = x.y; acc[jj][dq * 4 + 2] = x.z; acc[jj][dq * 4 + 3] = x.w;
                     }
                 }
         }
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * NC);
-        // kModeA: this warp's coefficients inside a stage: [q][jh*4 + jj][lane]
-        const uint32_t coef_off = (uint32_t)kTcOperandBytes + (uint32_t)((q * kTcJW + jh * JPW) * kLanes + lane) * 4u;
+        // kModeA: this warp's coefficients inside a stage: [q: 1 KB per lane tile][jh*JPW + jj][lane]
+        const uint32_t coef_off = (uint32_t)kTcOperandBytes + (uint32_t)((q * 8 + jh * JPW) * kLanes + lane) * 4u;
         int s = 0;
         uint32_t sph = 0;
         if (MODE == kModeAUniform) {
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 #pragma unroll
                 for (int jj = 0; jj < JPW; ++jj)
 #pragma unroll
-                    for (int d = 0; d < 16; ++d) acc[jj][d] = uh[jj * 16 + d];
+                    for (int d = 0; d < DD; ++d) acc[jj][d] = uh[jj * DD + d];
             }
         } else
         for (int n = 0; n < n_i; ++n) {
@@ -427,12 +432,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
             if (MODE == kModeL) {
 #pragma unroll
                 for (int jj = 0; jj < JPW; ++jj) {
-                    // four partial sums in two FFMA2 chains (half the FMA instructions, chains of 4 instead of 16)
+                    // four partial sums in two FFMA2 chains (half the FMA instructions, chains of DD/4 instead of DD)
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-                    for (int d = 0; d < 16; d += 4) {
-                        ffma2(d0, d1, uh[jj * 16 + d], uh[jj * 16 + d + 1], acc[jj][d], acc[jj][d + 1]);
-                        ffma2(d2, d3, uh[jj * 16 + d + 2], uh[jj * 16 + d + 3], acc[jj][d + 2], acc[jj][d + 3]);
+                    for (int d = 0; d < DD; d += 4) {
+                        ffma2(d0, d1, uh[jj * DD + d], uh[jj * DD + d + 1], acc[jj][d], acc[jj][d + 1]);
+                        ffma2(d2, d3, uh[jj * DD + d + 2], uh[jj * DD + d + 3], acc[jj][d + 2], acc[jj][d + 3]);
                     }
                     const float dot = (d0 + d1) + (d2 + d3);
                     if (tvalid && j0 + jj < p.C && !(p.dbg & 1)) p.out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = dot;
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                 for (int jj = 0; jj < JPW; ++jj) {
                     const float f = cc[jj];
 #pragma unroll
-                    for (int d = 0; d < 16; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f, f, uh[jj * 16 + d], uh[jj * 16 + d + 1]);
+                    for (int d = 0; d < DD; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f, f, uh[jj * DD + d], uh[jj * DD + d + 1]);
                 }
             }
             if (MODE == kModeA) {
@@ -457,8 +462,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
             for (int jj = 0; jj < JPW; ++jj)
                 if (j0 + jj < p.C) {
 #pragma unroll
-                    for (int dq = 0; dq < 4; ++dq)
-                        st4(p.out + (((((size_t)blockIdx.x * p.nbt + tile) * p.C + j0 + jj) * 4 + dq) * kLanes + lane) * 4,
+                    for (int dq = 0; dq < D4; ++dq)
+                        st4(p.out + (((((size_t)blockIdx.x * p.nbt + tile) * p.C + j0 + jj) * D4 + dq) * kLanes + lane) * 4,
                             make_float4(acc[jj][dq * 4 + 0], acc[jj][dq * 4 + 1], acc[jj][dq * 4 + 2], acc[jj][dq * 4 + 3]));
                 }
         }
@@ -479,7 +484,7 @@ int g_tc_stages = 10;
 int g_tc_dbg = 0;
 
 size_t tc_ua_floats(int B, int N) { return (size_t)cdiv(B > 0 ? B : 1, 128) * N * 2048; }
-size_t tc_wb_floats(int N, int C) { return (size_t)N * cdiv(C, kTcJW) * 2048; }
+size_t tc_wb_floats(int N, int C, int D) { return (size_t)N * cdiv(C, 128 / D) * 2048; }
 
 int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st) {
     const int ntq = cdiv(pl.B, 128);
@@ -490,9 +495,9 @@ int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st)
 }
 
 int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st) {
-    const int JG = cdiv(pl.C, kTcJW);
+    const int JG = cdiv(pl.C, 128 / pl.D);
     const long nw = (long)pl.N * JG * 128;
-    k_prep_w_tc<<<cdiv(nw, 256), 256, 0, st>>>(W, wb, pl.N, pl.C, JG);
+    k_prep_w_tc<<<cdiv(nw, 256), 256, 0, st>>>(W, wb, pl.N, pl.C, JG, pl.D);
     LAUNCH_CHECK();
     return 0;
 }
@@ -500,23 +505,26 @@ int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st)
 int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st) {
     PassTcParams tp{};
     tp.ua = ua; tp.wb = wb; tp.coef = pp.coef; tp.X = pp.X; tp.out = pp.out;
-    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, kTcJW); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
+    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, 128 / pl.D); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
     tp.dbg = g_tc_dbg;
     tp.ns = g_tc_stages < 2 ? 2 : g_tc_stages > kTcMaxStages ? kTcMaxStages : g_tc_stages;
     while ((size_t)tp.ns * tc_stage_bytes(mode) + 512 > 227 * 1024) --tp.ns;      // 227 KB of dynamic smem per CTA
     const size_t smem = (size_t)tp.ns * tc_stage_bytes(mode) + 512;
     dim3 grid(pl.IS, tp.JG, cdiv(pl.nbt, 4)), block(kTcThreads);
-#define CAPS_LAUNCH_TC(MODE)                                                                             \
+#define CAPS_LAUNCH_TC_D(MODE, DD)                                                                       \
     {                                                                                                    \
-        auto kern = k_pass_tc<MODE>;                                                                     \
+        auto kern = k_pass_tc<MODE, DD>;                                                                 \
         { static size_t attr_set = 0;   /* per instantiation; the attribute is per device function, set once (or when it grows) */ \
           if (smem > attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; } }    \
         kern<<<grid, block, smem, st>>>(tp);                                                             \
     }
+#define CAPS_LAUNCH_TC(MODE) { if (pl.D == 32) CAPS_LAUNCH_TC_D(MODE, 32) else CAPS_LAUNCH_TC_D(MODE, 16) }
+    if (pl.D != 16 && pl.D != 32) return fail(CAPS_E_UNSUPPORTED, "tcgen05 pass kernel: D must be 16 or 32");
     if (mode == kModeAUniform) CAPS_LAUNCH_TC(kModeAUniform)
     else if (mode == kModeA) CAPS_LAUNCH_TC(kModeA)
     else CAPS_LAUNCH_TC(kModeL)
 #undef CAPS_LAUNCH_TC
+#undef CAPS_LAUNCH_TC_D
     LAUNCH_CHECK();
     return 0;
 }
