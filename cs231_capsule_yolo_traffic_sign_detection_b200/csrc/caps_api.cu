@@ -81,10 +81,10 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     while (spt > 1 && p.nbt < spt) spt >>= 1;
     p.SPT = spt;
     p.ntg = cdiv(p.nbt, p.SPT);
-    p.use_tc = g_tune_tc != 0 && ((D == 16 && C >= 4) || (D == 32 && C >= 2));   // 128 / D capsules per tcgen05 CTA
+    p.use_tc = g_tune_tc != 0 && ((D == 16 && C >= 4) || ((D == 24 || D == 32) && C >= 2));   // tc_jw(D) capsules per tcgen05 CTA
     // split the i range until the grid fills the machine: the FMA kernel wants ~4 CTAs per SM, the tcgen05
     // kernel owns an SM (all of TMEM), so one wave of its CTAs (128-sample quads x 8-capsule groups) is enough
-    const long ctas = p.use_tc ? (long)cdiv(C, 128 / D) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
+    const long ctas = p.use_tc ? (long)cdiv(C, tc_jw(D)) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
     int is = g_tune_isplit > 0 ? g_tune_isplit : cdiv(4 * 148, ctas);
     if (g_tune_isplit <= 0 && p.use_tc) {
         // smallest split count (<= 32) whose grid wastes the least of its last wave of 148 CTAs

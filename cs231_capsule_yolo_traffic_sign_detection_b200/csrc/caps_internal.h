@@ -43,6 +43,7 @@ extern int g_tc_dbg;                    // timing experiments only
 extern int g_tc_stages;                 // smem ring depth of the tcgen05 pass kernel (tuning knob "tcstages")
 size_t tc_ua_floats(int B, int N);
 size_t tc_wb_floats(int N, int C, int D);
+int tc_jw(int D);
 int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st);
 int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st);
 int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st);

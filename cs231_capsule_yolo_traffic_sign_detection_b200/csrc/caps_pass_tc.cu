@@ -156,6 +156,26 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 template <int NC> __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NC]);
 template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld<64>(uint32_t taddr, float (&v)[64]) { tmem_ld64(taddr, v); }
+// 48 columns (two 24-d capsules): x32 + x16, one wait
+template <> __device__ __forceinline__ void tmem_ld<48>(uint32_t taddr, float (&v)[48]) {
+    uint32_t r[48];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47])
+        : "r"(taddr + 32));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 48; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
@@ -190,8 +210,8 @@ __global__ void k_prep_u_tc(const float* __restrict__ u, float* __restrict__ ua,
     }
 }
 
-// W [N][C][8][D] -> wb [N][JG][hi/lo][kq][128 rows][4]  (D = 16 or 32, 128/D capsules per group;
-// row n = D*(j - (128/D)*jg) + d; 4 = k % 4)
+// W [N][C][8][D] -> wb [N][JG][hi/lo][kq][128 rows][4]  (D = 16, 24 or 32; tc_jw(D) = 8, 4, 4 capsules per group;
+// row n = D*(j - tc_jw*jg) + d, rows >= tc_jw*D are zero; 4 = k % 4)
 __global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb, int N, int C, int JG, int D) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * JG * 128) return;
@@ -199,7 +219,8 @@ __global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb,
     const long ig = idx >> 7;
     const int jg = (int)(ig % JG);
     const long i = ig / JG;
-    const int j = jg * (128 / D) + n / D, d = n % D;
+    const int JW = D == 16 ? 8 : 4;
+    const int j = n < JW * D ? jg * JW + n / D : C, d = n % D;
     float* dst = wb + (size_t)ig * 2048 + n * 4;
 #pragma unroll
     for (int kq = 0; kq < 2; ++kq) {
@@ -227,11 +248,11 @@ struct PassTcParams {
     int dbg;             // TIMING EXPERIMENTS ONLY (tuning knob "tcdbg"): 1 = skip the L-mode stores, 2 = skip the coefficient copies
 };
 
-// DD = class-capsule dimension: 16 (8 capsules per CTA, 4 per epilogue warp) or 32 (4 per CTA, 2 per warp); the MMA
-// tile, the TMEM layout and the 64 accumulator columns per epilogue warp are the same for both.
+// DD = class-capsule dimension: 16 (8 capsules per CTA, 4 per epilogue warp), 24 or 32 (4 per CTA, 2 per warp).  The
+// MMA is M = 128, N = JW * DD (128, 96, 128); accumulators stay 128 TMEM columns apart.
 template <int MODE, int DD>
 __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
-    constexpr int JW = 128 / DD;
+    constexpr int JW = DD == 16 ? 8 : 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int ns = p.ns;
     constexpr int kTcStageBytes = tc_stage_bytes(MODE);
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
     } else if (warp >= kTcEpiWarps + kTcIssuers) {
         // ===== MMA issuer: the whole warp runs the loop converged, one elected lane issues =====
         // kind::tf32, D = f32, A/B K-major, N = 128, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((JW * DD) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         // descriptors differ between stages only in the 14-bit start-address field (bytes >> 4)
         const uint64_t desc0 = umma_desc(stages, 2048, 128);
         // issuer w takes stages n = w, w + NI, ...: stages are independent (own smem slot, own accumulator), and a
@@ -367,7 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
     } else {
         // ===== epilogue: warp w -> samples of lane tile 4*tq + w%4, capsules j0 .. j0+JPW-1 =====
         constexpr int JPW = JW / (kTcEpiWarps / 4), NC = DD * JPW, D4 = DD / 4;
-        static_assert(NC == 64, "64 accumulator columns per epilogue warp");
+        static_assert(NC == 64 || NC == 48, "64 (48 for D = 24) accumulator columns per epilogue warp");
         const int q = warp & 3, jh = warp >> 2;
         const int tile = tq * 4 + q;
         const bool tvalid = tile < p.nbt;
@@ -484,7 +505,8 @@ int g_tc_stages = 10;
 int g_tc_dbg = 0;
 
 size_t tc_ua_floats(int B, int N) { return (size_t)cdiv(B > 0 ? B : 1, 128) * N * 2048; }
-size_t tc_wb_floats(int N, int C, int D) { return (size_t)N * cdiv(C, 128 / D) * 2048; }
+int tc_jw(int D) { return D == 16 ? 8 : 4; }     // capsules per tcgen05 CTA (D = 16, 24, 32)
+size_t tc_wb_floats(int N, int C, int D) { return (size_t)N * cdiv(C, tc_jw(D)) * 2048; }
 
 int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st) {
     const int ntq = cdiv(pl.B, 128);
@@ -495,7 +517,7 @@ int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st)
 }
 
 int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st) {
-    const int JG = cdiv(pl.C, 128 / pl.D);
+    const int JG = cdiv(pl.C, tc_jw(pl.D));
     const long nw = (long)pl.N * JG * 128;
     k_prep_w_tc<<<cdiv(nw, 256), 256, 0, st>>>(W, wb, pl.N, pl.C, JG, pl.D);
     LAUNCH_CHECK();
@@ -505,7 +527,7 @@ int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st)
 int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st) {
     PassTcParams tp{};
     tp.ua = ua; tp.wb = wb; tp.coef = pp.coef; tp.X = pp.X; tp.out = pp.out;
-    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, 128 / pl.D); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
+    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, tc_jw(pl.D)); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
     tp.dbg = g_tc_dbg;
     tp.ns = g_tc_stages < 2 ? 2 : g_tc_stages > kTcMaxStages ? kTcMaxStages : g_tc_stages;
     while ((size_t)tp.ns * tc_stage_bytes(mode) + 512 > 227 * 1024) --tp.ns;      // 227 KB of dynamic smem per CTA
@@ -518,8 +540,8 @@ int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* 
           if (smem > attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; } }    \
         kern<<<grid, block, smem, st>>>(tp);                                                             \
     }
-#define CAPS_LAUNCH_TC(MODE) { if (pl.D == 32) CAPS_LAUNCH_TC_D(MODE, 32) else CAPS_LAUNCH_TC_D(MODE, 16) }
-    if (pl.D != 16 && pl.D != 32) return fail(CAPS_E_UNSUPPORTED, "tcgen05 pass kernel: D must be 16 or 32");
+#define CAPS_LAUNCH_TC(MODE) { if (pl.D == 32) CAPS_LAUNCH_TC_D(MODE, 32) else if (pl.D == 24) CAPS_LAUNCH_TC_D(MODE, 24) else CAPS_LAUNCH_TC_D(MODE, 16) }
+    if (pl.D != 16 && pl.D != 24 && pl.D != 32) return fail(CAPS_E_UNSUPPORTED, "tcgen05 pass kernel: D must be 16, 24 or 32");
     if (mode == kModeAUniform) CAPS_LAUNCH_TC(kModeAUniform)
     else if (mode == kModeA) CAPS_LAUNCH_TC(kModeA)
     else CAPS_LAUNCH_TC(kModeL)

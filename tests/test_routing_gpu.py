@@ -74,6 +74,8 @@ def test_golden_fixture(capsb, name):
     (40, 96, 43, 8, 32, 5),       # sweep corner: D=32, R=5
     (3, 7, 3, 8, 4, 3),           # tiny / odd everything
     (2, 9, 2, 8, 24, 2),
+    (70, 200, 43, 8, 24, 3),      # sweep corner: D=24 (tcgen05 passes with N = 96, FMA gradient sweep)
+    (130, 64, 5, 8, 32, 2),       # D=32, two j-groups, second one ragged
 ])
 def test_against_c_oracle_fp64(capsb, dims):
     from oracle import routing_c as oc
