@@ -117,7 +117,7 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.o_beta = o; o += p.with_grad ? p.cs * (p.Reff > 1 ? p.Reff - 1 : 0) : 0;
     p.o_tmp = o; o += p.with_grad && p.Reff > 1 ? p.cs : 0;
     p.o_ds = o; o += p.with_grad ? p.xs * p.Reff : 0;
-    p.o_dupart = o; o += p.with_grad ? p.us * p.JG : 0;
+    p.o_dupart = o; o += p.with_grad ? p.us * std::max(p.JG, cdiv(C * (p.DP / 16 > 0 ? p.DP / 16 : 1), 8)) : 0;   // FMA kernel: JG partials; mma kernel: <= cdiv(C * D/16, 8)
     p.total = o;
     return true;
 }
@@ -343,7 +343,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     int rc;
     // The mma gradient kernel wants ds^0 pre-multiplied by iteration 0's uniform coupling 1/C (ds^0 has no other
     // reader); the FMA kernel multiplies by cconst[0] itself.  Same fp32 product either way.
-    const bool grad_mma = g_tune_gradmma && pl.DP == 16 && pl.D == 16 && pl.JW == 8;
+    const bool grad_mma = g_tune_gradmma && (pl.D == 16 || pl.D == 32) && pl.JW == 8;
     const float ds0_scale = grad_mma ? 1.f / (float)C : 1.f;
     // top: dv = grad_v + margin gradient ; ds^{R-1}
     if ((rc = launch_dsquash(pl, nullptr, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),
@@ -404,7 +404,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     if (rc) return rc;
     if (du != nullptr) {
         const long n = (long)pl.nbt * N * 32;
-        const int parts = grad_mma ? cdiv(C, grad_mma_jw(pl)) : pl.JG;
+        const int parts = grad_mma ? grad_mma_parts(pl) : pl.JG;
         { LaunchScope ls_(kcReduceDu, st); k_reduce_du<8><<<cdiv(n, 128), 128, 0, st>>>(gp.du_part, parts, du, B, N, pl.nbt); }
         LAUNCH_CHECK();
     }

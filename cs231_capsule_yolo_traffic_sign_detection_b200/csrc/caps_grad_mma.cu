@@ -153,10 +153,16 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
     const int i0 = blockIdx.x * IT;
     const int ni = min(IT, p.N - i0);
-    const int j0 = blockIdx.y * JW;
-    const int j = j0 + warp;
-    const bool jvalid = j < p.C;
-    const int njv = min(JW, p.C - j0);
+    // D = 32: every capsule is two 16-dim "pseudo-capsules" (j, h): same coefficients, X / W / dW columns 16 h .. 16 h + 15.
+    // dW of the halves is independent and du is a sum over (j, d) anyway, so a warp simply owns one pseudo-capsule.
+    const int hs = (p.D >> 4) - 1;                         // 0 (D = 16) or 1 (D = 32): pseudo-capsule = 2 j + h
+    const int jp0 = blockIdx.y * JW;
+    const int j = (jp0 + warp) >> hs, h = (jp0 + warp) & hs;
+    const bool jvalid = jp0 + warp < (p.C << hs);
+    const int njv = min(JW, (p.C << hs) - jp0);            // valid pseudo-capsules (warps) of this CTA
+    const int jfirst = jp0 >> hs;                          // the CTA's capsules jfirst .. jfirst + njr - 1: coefficient rows
+    const int njr = min(p.C, ((jp0 + JW - 1) >> hs) + 1) - jfirst;
+    const int D4 = p.D >> 2;
 
     // W^T fragments for du:  B[d][k] = W[k][d];  b0 = (d = t + 8 ks, k = g), b1 = (d = t + 4 + 8 ks, k = g)
     for (int e = threadIdx.x; e < IT * JW * 64; e += blockDim.x) {
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
         const int gg = l >> 2, tt = l & 3;
         float w0 = 0.f, w1 = 0.f;
         if (il < ni && w < njv) {
-            const float* row = p.W + ((size_t)(i0 + il) * p.C + j0 + w) * 128 + gg * 16;      // W[i][j][k = gg][:]
+            const float* row = p.W + (((size_t)(i0 + il) * p.C + ((jp0 + w) >> hs)) * 8 + gg) * p.D + ((jp0 + w) & hs) * 16;   // W[i][j][k = gg][16 h ..]
             w0 = __ldg(row + tt + 8 * ks);
             w1 = __ldg(row + tt + 4 + 8 * ks);
         }
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
         // ===== service warp: (1) one elected lane streams (tile, il) stages into the ring, NS ahead;
         // (2) the whole warp sums the consumer warps' du fragments of each finished round and writes the CTA's
         // partial -- so the consumers never meet at a CTA barrier.  Event loop over the two non-blocking waits.
-        const uint32_t ubytes = 2 * 32 * 4 * 4, cbytes = (uint32_t)njv * 128u;
+        const uint32_t ubytes = 2 * 32 * 4 * 4, cbytes = (uint32_t)njr * 128u;
         int ncoef = 0;
 #pragma unroll
         for (int m = 0; m < M; ++m) ncoef += p.coef[m] != nullptr;
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     for (int m = 0; m < M; ++m)
                         if (p.coef[m] != nullptr) {
                             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                         ::"r"(cd), "l"(p.coef[m] + (ti * p.C + j0) * kLanes), "r"(cbytes), "r"(bar) : "memory");
+                                         ::"r"(cd), "l"(p.coef[m] + (ti * p.C + jfirst) * kLanes), "r"(cbytes), "r"(bar) : "memory");
                             cd += JW * 128;
                         }
                 }
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                 // FMAs, needs a second register set for X and spills
                 asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
                              : "=f"(xr[m][dq * 4 + 0]), "=f"(xr[m][dq * 4 + 1]), "=f"(xr[m][dq * 4 + 2]), "=f"(xr[m][dq * 4 + 3])
-                             : "l"(p.X[m] + ((((size_t)tile * p.C + j) * 4 + dq) * kLanes + lane) * 4) : "memory");
+                             : "l"(p.X[m] + ((((size_t)tile * p.C + j) * D4 + h * 4 + dq) * kLanes + lane) * 4) : "memory");
             }
     };
     if (jvalid) load_x(0);
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     float G[16];
 #pragma unroll
                     for (int d = 0; d < 16; ++d) G[d] = xr[0][d];
-                    const float* crow = stg + 272 + warp * 32 + lane;
+                    const float* crow = stg + 272 + (j - jfirst) * 32 + lane;
 #pragma unroll
                     for (int m = 1; m < M; ++m) {
                         const float al = crow[(m - 1) * JW * 32];
@@ -362,11 +368,11 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     if (jvalid)
         for (int il = 0; il < ni; ++il) {
             const float4 v = *reinterpret_cast<const float4*>(dWsm + (size_t)((il * JW + warp) * 32 + lane) * 4);
-            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j) * 128;
-            dst[(2 * t) * 16 + g] = v.x;
-            dst[(2 * t + 1) * 16 + g] = v.y;
-            dst[(2 * t) * 16 + g + 8] = v.z;
-            dst[(2 * t + 1) * 16 + g + 8] = v.w;
+            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j) * 8 * p.D + h * 16;
+            dst[(2 * t) * p.D + g] = v.x;
+            dst[(2 * t + 1) * p.D + g] = v.y;
+            dst[(2 * t) * p.D + g + 8] = v.z;
+            dst[(2 * t + 1) * p.D + g + 8] = v.w;
         }
 }
 
@@ -377,7 +383,7 @@ int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     auto kern = k_grad_mma<M, JW>;
     { static bool attr_set = false;
       if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; } }
-    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C, JW)), block(32 * JW + 32);
+    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * (pl.D / 16), JW)), block(32 * JW + 32);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();
     return 0;
@@ -404,7 +410,10 @@ int g_grad_jw = 0;   // tuning knob "gradjw": 0 = auto, 8 or 11
 // C = 43); 8 stays selectable for experiments and as a second summation grouping in the tests.
 int grad_mma_jw(const Plan&) { return g_grad_jw == 8 ? 8 : 11; }
 
-// D == 16, K == 8, C >= 7, R <= 5.  Writes cdiv(C, grad_mma_jw(pl)) du partials.
+// du partials the kernel writes (one per CTA row)
+int grad_mma_parts(const Plan& pl) { return cdiv(pl.C * (pl.D / 16), grad_mma_jw(pl)); }
+
+// D == 16 or 32, K == 8, R <= 5.  Writes grad_mma_parts(pl) du partials.
 int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     return grad_mma_jw(pl) == 11 ? launch_m<11>(pl, gp, st) : launch_m<8>(pl, gp, st);
 }

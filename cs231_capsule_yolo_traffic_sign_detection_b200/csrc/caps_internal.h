@@ -36,7 +36,8 @@ struct Plan {
 int launch_pass(const Plan& pl, int mode, const PassParams& pp, cudaStream_t st);   // caps_pass.cu
 int launch_grad(const Plan& pl, const GradParams& gp, cudaStream_t st);             // caps_grad.cu
 int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st);         // caps_grad_mma.cu (D == 16, C >= 7)
-int grad_mma_jw(const Plan& pl);           // output capsules per CTA it will use (8 or 11): it writes cdiv(C, jw) du partials
+int grad_mma_jw(const Plan& pl);           // output (pseudo-)capsules per CTA it will use (8 or 11)
+int grad_mma_parts(const Plan& pl);        // du partials it writes: cdiv(C * D/16, jw)
 extern int g_grad_jw;                      // tuning knob "gradjw": 0 = auto
 // caps_pass_tc.cu: tcgen05 pass kernel (D == 16 only) and its operand preparation
 extern int g_tc_dbg;                    // timing experiments only
