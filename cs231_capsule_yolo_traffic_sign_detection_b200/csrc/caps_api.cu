@@ -81,10 +81,11 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     while (spt > 1 && p.nbt < spt) spt >>= 1;
     p.SPT = spt;
     p.ntg = cdiv(p.nbt, p.SPT);
-    p.use_tc = g_tune_tc != 0 && ((D == 16 && C >= 4) || ((D == 24 || D == 32) && C >= 2));   // tc_jw(D) capsules per tcgen05 CTA
+    // tc_jw(DP) capsules per tcgen05 CTA; D < DP (21 -> 24, 9..15 -> 16, ...) runs on the zero-padded W copy
+    p.use_tc = g_tune_tc != 0 && p.DP >= 16 && C >= 2 && (p.DP != 16 || C >= 4);
     // split the i range until the grid fills the machine: the FMA kernel wants ~4 CTAs per SM, the tcgen05
     // kernel owns an SM (all of TMEM), so one wave of its CTAs (128-sample quads x 8-capsule groups) is enough
-    const long ctas = p.use_tc ? (long)cdiv(C, tc_jw(D)) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
+    const long ctas = p.use_tc ? (long)cdiv(C, tc_jw(p.DP)) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
     int is = g_tune_isplit > 0 ? g_tune_isplit : cdiv(4 * 148, ctas);
     if (g_tune_isplit <= 0 && p.use_tc) {
         // smallest split count (<= 32) whose grid wastes the least of its last wave of 148 CTAs
@@ -106,7 +107,7 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.us = round64((size_t)p.nbt * N * K * 32);
     size_t o = 0;
     p.o_ua = o; o += p.use_tc ? round64(tc_ua_floats(B, N)) : 0;
-    p.o_wb = o; o += p.use_tc ? round64(tc_wb_floats(N, C, D)) : 0;
+    p.o_wb = o; o += p.use_tc ? round64(tc_wb_floats(N, C, p.DP)) : 0;
     p.o_ut = o; o += p.us;
     p.o_wp = o; o += p.pad_w ? round64((size_t)N * C * K * p.DP) : 0;
     p.o_vsum = o; o += p.xs;
@@ -274,7 +275,7 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
         int rc;
         { LaunchScope ls_(kcLayout, st); rc = launch_prep_u_tc(pl, u, w + pl.o_ua, st); }
         if (rc) return rc;
-        { LaunchScope ls_(kcLayout, st); rc = launch_prep_w_tc(pl, W, w + pl.o_wb, st); }
+        { LaunchScope ls_(kcLayout, st); rc = launch_prep_w_tc(pl, Wp, w + pl.o_wb, st); }
         if (rc) return rc;
     }
     float* vsum = w + pl.o_vsum;

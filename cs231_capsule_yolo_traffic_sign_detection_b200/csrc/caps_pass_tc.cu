@@ -210,7 +210,8 @@ __global__ void k_prep_u_tc(const float* __restrict__ u, float* __restrict__ ua,
     }
 }
 
-// W [N][C][8][D] -> wb [N][JG][hi/lo][kq][128 rows][4]  (D = 16, 24 or 32; tc_jw(D) = 8, 4, 4 capsules per group;
+// W [N][C][8][D] -> wb [N][JG][hi/lo][kq][128 rows][4]  (D = 16, 24, 32 or 48 -- the PADDED dimension, W being the padded
+// copy when the public D is smaller; tc_jw(D) = 8, 4, 4, 2 capsules per group;
 // row n = D*(j - tc_jw*jg) + d, rows >= tc_jw*D are zero; 4 = k % 4)
 __global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb, int N, int C, int JG, int D) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +220,7 @@ __global__ void k_prep_w_tc(const float* __restrict__ W, float* __restrict__ wb,
     const long ig = idx >> 7;
     const int jg = (int)(ig % JG);
     const long i = ig / JG;
-    const int JW = D == 16 ? 8 : 4;
+    const int JW = D == 16 ? 8 : D == 48 ? 2 : 4;
     const int j = n < JW * D ? jg * JW + n / D : C, d = n % D;
     float* dst = wb + (size_t)ig * 2048 + n * 4;
 #pragma unroll
@@ -248,11 +249,11 @@ struct PassTcParams {
     int dbg;             // TIMING EXPERIMENTS ONLY (tuning knob "tcdbg"): 1 = skip the L-mode stores, 2 = skip the coefficient copies
 };
 
-// DD = class-capsule dimension: 16 (8 capsules per CTA, 4 per epilogue warp), 24 or 32 (4 per CTA, 2 per warp).  The
-// MMA is M = 128, N = JW * DD (128, 96, 128); accumulators stay 128 TMEM columns apart.
+// DD = (padded) class-capsule dimension: 16 (8 capsules per CTA, 4 per epilogue warp), 24 or 32 (4 per CTA, 2 per warp),
+// 48 (2 per CTA, 1 per warp).  The MMA is M = 128, N = JW * DD (128, 96, 128, 96); accumulators stay 128 TMEM columns apart.
 template <int MODE, int DD>
 __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
-    constexpr int JW = DD == 16 ? 8 : 4;
+    constexpr int JW = DD == 16 ? 8 : DD == 48 ? 2 : 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int ns = p.ns;
     constexpr int kTcStageBytes = tc_stage_bytes(MODE);
@@ -505,7 +506,7 @@ int g_tc_stages = 10;
 int g_tc_dbg = 0;
 
 size_t tc_ua_floats(int B, int N) { return (size_t)cdiv(B > 0 ? B : 1, 128) * N * 2048; }
-int tc_jw(int D) { return D == 16 ? 8 : 4; }     // capsules per tcgen05 CTA (D = 16, 24, 32)
+int tc_jw(int D) { return D == 16 ? 8 : D == 48 ? 2 : 4; }     // capsules per tcgen05 CTA (padded D = 16, 24, 32, 48)
 size_t tc_wb_floats(int N, int C, int D) { return (size_t)N * cdiv(C, tc_jw(D)) * 2048; }
 
 int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st) {
@@ -517,9 +518,9 @@ int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, cudaStream_t st)
 }
 
 int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st) {
-    const int JG = cdiv(pl.C, tc_jw(pl.D));
+    const int JG = cdiv(pl.C, tc_jw(pl.DP));              // W: the padded copy ([N][C][8][DP]) when D < DP
     const long nw = (long)pl.N * JG * 128;
-    k_prep_w_tc<<<cdiv(nw, 256), 256, 0, st>>>(W, wb, pl.N, pl.C, JG, pl.D);
+    k_prep_w_tc<<<cdiv(nw, 256), 256, 0, st>>>(W, wb, pl.N, pl.C, JG, pl.DP);
     LAUNCH_CHECK();
     return 0;
 }
@@ -527,7 +528,7 @@ int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st)
 int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st) {
     PassTcParams tp{};
     tp.ua = ua; tp.wb = wb; tp.coef = pp.coef; tp.X = pp.X; tp.out = pp.out;
-    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, tc_jw(pl.D)); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
+    tp.N = pl.N; tp.C = pl.C; tp.JG = cdiv(pl.C, tc_jw(pl.DP)); tp.nbt = pl.nbt; tp.i_per_split = pl.i_per_split;
     tp.dbg = g_tc_dbg;
     tp.ns = g_tc_stages < 2 ? 2 : g_tc_stages > kTcMaxStages ? kTcMaxStages : g_tc_stages;
     while ((size_t)tp.ns * tc_stage_bytes(mode) + 512 > 227 * 1024) --tp.ns;      // 227 KB of dynamic smem per CTA
@@ -540,8 +541,10 @@ int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* 
           if (smem > attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; } }    \
         kern<<<grid, block, smem, st>>>(tp);                                                             \
     }
-#define CAPS_LAUNCH_TC(MODE) { if (pl.D == 32) CAPS_LAUNCH_TC_D(MODE, 32) else if (pl.D == 24) CAPS_LAUNCH_TC_D(MODE, 24) else CAPS_LAUNCH_TC_D(MODE, 16) }
-    if (pl.D != 16 && pl.D != 24 && pl.D != 32) return fail(CAPS_E_UNSUPPORTED, "tcgen05 pass kernel: D must be 16, 24 or 32");
+#define CAPS_LAUNCH_TC(MODE)                                                                             \
+    { if (pl.DP == 48) CAPS_LAUNCH_TC_D(MODE, 48) else if (pl.DP == 32) CAPS_LAUNCH_TC_D(MODE, 32)       \
+      else if (pl.DP == 24) CAPS_LAUNCH_TC_D(MODE, 24) else CAPS_LAUNCH_TC_D(MODE, 16) }
+    if (pl.DP != 16 && pl.DP != 24 && pl.DP != 32 && pl.DP != 48) return fail(CAPS_E_UNSUPPORTED, "tcgen05 pass kernel: padded D must be 16, 24, 32 or 48");
     if (mode == kModeAUniform) CAPS_LAUNCH_TC(kModeAUniform)
     else if (mode == kModeA) CAPS_LAUNCH_TC(kModeA)
     else CAPS_LAUNCH_TC(kModeL)
