@@ -344,7 +344,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     int rc;
     // The mma gradient kernel wants ds^0 pre-multiplied by iteration 0's uniform coupling 1/C (ds^0 has no other
     // reader); the FMA kernel multiplies by cconst[0] itself.  Same fp32 product either way.
-    const bool grad_mma = g_tune_gradmma && (pl.D == 16 || pl.D == 32) && pl.JW == 8;
+    const bool grad_mma = g_tune_gradmma && (pl.D == 16 || pl.D == 32 || pl.D == 48) && pl.JW == 8;
     const float ds0_scale = grad_mma ? 1.f / (float)C : 1.f;
     // top: dv = grad_v + margin gradient ; ds^{R-1}
     if ((rc = launch_dsquash(pl, nullptr, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),

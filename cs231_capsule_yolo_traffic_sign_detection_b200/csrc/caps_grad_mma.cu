@@ -153,15 +153,15 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
     const int i0 = blockIdx.x * IT;
     const int ni = min(IT, p.N - i0);
-    // D = 32: every capsule is two 16-dim "pseudo-capsules" (j, h): same coefficients, X / W / dW columns 16 h .. 16 h + 15.
-    // dW of the halves is independent and du is a sum over (j, d) anyway, so a warp simply owns one pseudo-capsule.
-    const int hs = (p.D >> 4) - 1;                         // 0 (D = 16) or 1 (D = 32): pseudo-capsule = 2 j + h
+    // D = 32 / 48: every capsule is two / three 16-dim "pseudo-capsules" (j, h): same coefficients, X / W / dW columns
+    // 16 h .. 16 h + 15.  dW of the parts is independent and du is a sum over (j, d) anyway, so a warp simply owns one.
+    const int DH = p.D >> 4;                               // 1, 2, 3: pseudo-capsule index = DH j + h
     const int jp0 = blockIdx.y * JW;
-    const int j = (jp0 + warp) >> hs, h = (jp0 + warp) & hs;
-    const bool jvalid = jp0 + warp < (p.C << hs);
-    const int njv = min(JW, (p.C << hs) - jp0);            // valid pseudo-capsules (warps) of this CTA
-    const int jfirst = jp0 >> hs;                          // the CTA's capsules jfirst .. jfirst + njr - 1: coefficient rows
-    const int njr = min(p.C, ((jp0 + JW - 1) >> hs) + 1) - jfirst;
+    const int j = (jp0 + warp) / DH, h = (jp0 + warp) - j * DH;
+    const bool jvalid = jp0 + warp < p.C * DH;
+    const int njv = min(JW, p.C * DH - jp0);               // valid pseudo-capsules (warps) of this CTA
+    const int jfirst = jp0 / DH;                           // the CTA's capsules jfirst .. jfirst + njr - 1: coefficient rows
+    const int njr = min(p.C, (jp0 + JW - 1) / DH + 1) - jfirst;
     const int D4 = p.D >> 2;
 
     // W^T fragments for du:  B[d][k] = W[k][d];  b0 = (d = t + 8 ks, k = g), b1 = (d = t + 4 + 8 ks, k = g)
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
         const int gg = l >> 2, tt = l & 3;
         float w0 = 0.f, w1 = 0.f;
         if (il < ni && w < njv) {
-            const float* row = p.W + (((size_t)(i0 + il) * p.C + ((jp0 + w) >> hs)) * 8 + gg) * p.D + ((jp0 + w) & hs) * 16;   // W[i][j][k = gg][16 h ..]
+            const int jw = (jp0 + w) / DH, hw = (jp0 + w) - jw * DH;
+            const float* row = p.W + (((size_t)(i0 + il) * p.C + jw) * 8 + gg) * p.D + hw * 16;   // W[i][j][k = gg][16 h ..]
             w0 = __ldg(row + tt + 8 * ks);
             w1 = __ldg(row + tt + 4 + 8 * ks);
         }
@@ -413,7 +414,7 @@ int grad_mma_jw(const Plan&) { return g_grad_jw == 8 ? 8 : 11; }
 // du partials the kernel writes (one per CTA row)
 int grad_mma_parts(const Plan& pl) { return cdiv(pl.C * (pl.D / 16), grad_mma_jw(pl)); }
 
-// D == 16 or 32, K == 8, R <= 5.  Writes grad_mma_parts(pl) du partials.
+// D == 16, 32 or 48, K == 8, R <= 5.  Writes grad_mma_parts(pl) du partials.
 int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     return grad_mma_jw(pl) == 11 ? launch_m<11>(pl, gp, st) : launch_m<8>(pl, gp, st);
 }

@@ -155,12 +155,12 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
 /* Tuning knobs (process-wide, read at call time; defaults are chosen per shape).
  *   name = "spt"  samples per thread in the pass kernels (1, 2 or 4; 0 = auto)
  *   name = "isplit" forced number of splits of the N range (0 = auto)
- *   name = "tc"   1 (default): tcgen05 tensor-core pass kernel where it applies (D == 16 and C >= 4, or
- *                 D == 24 / 32 and C >= 2);
+ *   name = "tc"   1 (default): tcgen05 tensor-core pass kernel where it applies (9 <= D <= 16 and C >= 4, or
+ *                 17 <= D <= 48 and C >= 2; D is zero-padded to 16 / 24 / 32 / 48);
  *                 0: fp32-FMA pass kernel everywhere
  *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
- *                 (D == 16 or 32, C >= 7); 0: fp32-FMA gradient kernel everywhere
+ *                 (D == 16, 32 or 48, C >= 7); 0: fp32-FMA gradient kernel everywhere
  *   name = "gradjw" output capsules per CTA of that kernel: 0 (default) auto, 8 or 11
  *   name = "hostmb" caps_route_step_host micro-batching: 0 (default) auto, 1 single batch
  *   name = "profile" 1: bracket every launch with CUDA events (see caps_profile_collect)
