@@ -118,7 +118,7 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.o_beta = o; o += p.with_grad ? p.cs * (p.Reff > 1 ? p.Reff - 1 : 0) : 0;
     p.o_tmp = o; o += p.with_grad && p.Reff > 1 ? p.cs : 0;
     p.o_ds = o; o += p.with_grad ? p.xs * p.Reff : 0;
-    p.o_dupart = o; o += p.with_grad ? p.us * std::max(p.JG, cdiv(C * (p.DP / 16 > 0 ? p.DP / 16 : 1), 8)) : 0;   // FMA kernel: JG partials; mma kernel: <= cdiv(C * D/16, 8)
+    p.o_dupart = o; o += p.with_grad ? p.us * std::max(p.JG, cdiv(C * cdiv(p.DP, 16), 8)) : 0;   // FMA kernel: JG partials; mma kernel: <= cdiv(C * D/16, 8)
     p.total = o;
     return true;
 }
@@ -344,7 +344,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     int rc;
     // The mma gradient kernel wants ds^0 pre-multiplied by iteration 0's uniform coupling 1/C (ds^0 has no other
     // reader); the FMA kernel multiplies by cconst[0] itself.  Same fp32 product either way.
-    const bool grad_mma = g_tune_gradmma && (pl.D == 16 || pl.D == 32 || pl.D == 48) && pl.JW == 8;
+    const bool grad_mma = g_tune_gradmma && pl.DP >= 16 && pl.JW == 8;       // D >= 9, C >= 7
     const float ds0_scale = grad_mma ? 1.f / (float)C : 1.f;
     // top: dv = grad_v + margin gradient ; ds^{R-1}
     if ((rc = launch_dsquash(pl, nullptr, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),
@@ -384,7 +384,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     }
     GradParams gp{};
     gp.ut = ut; gp.W = Wp; gp.dW = dW; gp.du_part = w + pl.o_dupart;
-    gp.N = N; gp.C = C; gp.D = D; gp.nbt = pl.nbt;
+    gp.N = N; gp.C = C; gp.D = D; gp.DP = pl.DP; gp.nbt = pl.nbt;
     int m = 0;
     for (int r = 0; r < Re; ++r) {                                          // c^r (x) ds^r
         gp.coef[m] = (r == 0) ? nullptr : w + pl.o_c + pl.cs * (r - 1);

@@ -134,8 +134,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // register-prefetched) loads the kernel ran at exactly one loaded-HBM latency (~1750 cycles) per unit
 // whatever the math did (11 ms with ALL the math removed): 8 warps with one unit of loads in flight each
 // is far too little memory-level parallelism.
-template <int M, int JW>
+// GEN = false: D == 16 exactly (the hot shapes): every dimension below is a compile-time constant.
+template <int M, int JW, bool GEN>
 __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
+    const int pD = GEN ? p.D : 16, pDP = GEN ? p.DP : 16;
     constexpr int IT = kGmIT, DUB = gm_dub(JW), NT = 32 * JW;     // NT: consumer threads
     constexpr int NS = gm_stages(M, JW), SF = gm_stage_floats(M, JW);    // stage: u tile + up to M-1 coefficient rows
     static_assert(NS >= 3, "operand ring too shallow");
@@ -153,16 +155,18 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
     const int i0 = blockIdx.x * IT;
     const int ni = min(IT, p.N - i0);
-    // D = 32 / 48: every capsule is two / three 16-dim "pseudo-capsules" (j, h): same coefficients, X / W / dW columns
+    // D > 16: every capsule is two / three 16-dim "pseudo-capsules" (j, h): same coefficients, X / W / dW columns
     // 16 h .. 16 h + 15.  dW of the parts is independent and du is a sum over (j, d) anyway, so a warp simply owns one.
-    const int DH = p.D >> 4;                               // 1, 2, 3: pseudo-capsule index = DH j + h
+    // Columns at or beyond the padded dimension DP (D = 24, 21: the second part has 8 real columns) read as zero;
+    // dW is only written for d < D.  W and the X arrays have rows of DP floats, dW (public) of D.
+    const int DH = GEN ? (pDP + 15) >> 4 : 1;              // 1, 2, 3: pseudo-capsule index = DH j + h
     const int jp0 = blockIdx.y * JW;
     const int j = (jp0 + warp) / DH, h = (jp0 + warp) - j * DH;
     const bool jvalid = jp0 + warp < p.C * DH;
     const int njv = min(JW, p.C * DH - jp0);               // valid pseudo-capsules (warps) of this CTA
     const int jfirst = jp0 / DH;                           // the CTA's capsules jfirst .. jfirst + njr - 1: coefficient rows
     const int njr = min(p.C, (jp0 + JW - 1) / DH + 1) - jfirst;
-    const int D4 = p.D >> 2;
+    const int D4 = pDP >> 2;
 
     // W^T fragments for du:  B[d][k] = W[k][d];  b0 = (d = t + 8 ks, k = g), b1 = (d = t + 4 + 8 ks, k = g)
     for (int e = threadIdx.x; e < IT * JW * 64; e += blockDim.x) {
@@ -171,9 +175,9 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
         float w0 = 0.f, w1 = 0.f;
         if (il < ni && w < njv) {
             const int jw = (jp0 + w) / DH, hw = (jp0 + w) - jw * DH;
-            const float* row = p.W + (((size_t)(i0 + il) * p.C + jw) * 8 + gg) * p.D + hw * 16;   // W[i][j][k = gg][16 h ..]
-            w0 = __ldg(row + tt + 8 * ks);
-            w1 = __ldg(row + tt + 4 + 8 * ks);
+            const float* row = p.W + (((size_t)(i0 + il) * p.C + jw) * 8 + gg) * pDP + hw * 16;   // W[i][j][k = gg][16 h ..]
+            if (hw * 16 + tt + 8 * ks < pDP) w0 = __ldg(row + tt + 8 * ks);
+            if (hw * 16 + tt + 4 + 8 * ks < pDP) w1 = __ldg(row + tt + 4 + 8 * ks);
         }
         // kept whole: the tensor core truncates its operands, so the "hi" half is w itself and lo = tf32_lo(w) at use
         *reinterpret_cast<float2*>(Wfrag + (size_t)((il * JW + w) * 2 + ks) * 64 + l * 2) = make_float2(w0, w1);
@@ -278,6 +282,10 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
         for (int m = 0; m < M; ++m)
 #pragma unroll
             for (int dq = 0; dq < 4; ++dq) {
+                if (GEN && h * 4 + dq >= D4) {              // beyond the padded dimension (warp-uniform)
+                    xr[m][dq * 4 + 0] = 0.f; xr[m][dq * 4 + 1] = 0.f; xr[m][dq * 4 + 2] = 0.f; xr[m][dq * 4 + 3] = 0.f;
+                    continue;
+                }
                 // volatile + "memory": must stay below the warp barrier it follows, or ptxas hoists it above the G
                 // FMAs, needs a second register set for X and spills
                 asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -369,11 +377,15 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     if (jvalid)
         for (int il = 0; il < ni; ++il) {
             const float4 v = *reinterpret_cast<const float4*>(dWsm + (size_t)((il * JW + warp) * 32 + lane) * 4);
-            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j) * 8 * p.D + h * 16;
-            dst[(2 * t) * p.D + g] = v.x;
-            dst[(2 * t + 1) * p.D + g] = v.y;
-            dst[(2 * t) * p.D + g + 8] = v.z;
-            dst[(2 * t + 1) * p.D + g + 8] = v.w;
+            float* dst = p.dW + ((size_t)(i0 + il) * p.C + j) * 8 * pD + h * 16;
+            if (h * 16 + g < pD) {
+                dst[(2 * t) * pD + g] = v.x;
+                dst[(2 * t + 1) * pD + g] = v.y;
+            }
+            if (h * 16 + g + 8 < pD) {
+                dst[(2 * t) * pD + g + 8] = v.z;
+                dst[(2 * t + 1) * pD + g + 8] = v.w;
+            }
         }
 }
 
@@ -381,10 +393,11 @@ template <int M, int JW>
 int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     const size_t smem = ((size_t)gm_fixed_floats(JW) + (size_t)gm_stages(M, JW) * gm_stage_floats(M, JW)) * sizeof(float) +
                         16 * gm_stages(M, JW) + 32;
-    auto kern = k_grad_mma<M, JW>;
-    { static bool attr_set = false;
-      if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; } }
-    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * (pl.D / 16), JW)), block(32 * JW + 32);
+    auto kern = pl.D == 16 ? k_grad_mma<M, JW, false> : k_grad_mma<M, JW, true>;
+    { static bool attr_set[2] = {false, false};
+      bool& done = attr_set[pl.D == 16 ? 0 : 1];
+      if (!done) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; } }
+    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * cdiv(pl.DP, 16), JW)), block(32 * JW + 32);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();
     return 0;
@@ -412,9 +425,9 @@ int g_grad_jw = 0;   // tuning knob "gradjw": 0 = auto, 8 or 11
 int grad_mma_jw(const Plan&) { return g_grad_jw == 8 ? 8 : 11; }
 
 // du partials the kernel writes (one per CTA row)
-int grad_mma_parts(const Plan& pl) { return cdiv(pl.C * (pl.D / 16), grad_mma_jw(pl)); }
+int grad_mma_parts(const Plan& pl) { return cdiv(pl.C * cdiv(pl.DP, 16), grad_mma_jw(pl)); }
 
-// D == 16, 32 or 48, K == 8, R <= 5.  Writes grad_mma_parts(pl) du partials.
+// 9 <= D <= 48, K == 8, R <= 5.  Writes grad_mma_parts(pl) du partials.
 int launch_grad_mma(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     return grad_mma_jw(pl) == 11 ? launch_m<11>(pl, gp, st) : launch_m<8>(pl, gp, st);
 }

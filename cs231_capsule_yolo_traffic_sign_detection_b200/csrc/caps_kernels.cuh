@@ -572,6 +572,7 @@ struct GradParams {
     const float* X[kGradMaxM];         // [nbt][C][D4][32][4]
     float cconst[kGradMaxM];
     int N, C, D, nbt;
+    int DP;                            // padded D: row length of W and of the X arrays (k_grad_mma)
 };
 
 // transpose-reduce: every lane holds 32 values; lane l returns sum over lanes of vals[l].

@@ -160,7 +160,7 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
  *                 0: fp32-FMA pass kernel everywhere
  *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
- *                 (D == 16, 32 or 48, C >= 7); 0: fp32-FMA gradient kernel everywhere
+ *                 (D >= 9, C >= 7); 0: fp32-FMA gradient kernel everywhere
  *   name = "gradjw" output capsules per CTA of that kernel: 0 (default) auto, 8 or 11
  *   name = "hostmb" caps_route_step_host micro-batching: 0 (default) auto, 1 single batch
  *   name = "profile" 1: bracket every launch with CUDA events (see caps_profile_collect)

@@ -77,6 +77,8 @@ def test_golden_fixture(capsb, name):
     (70, 200, 43, 8, 24, 3),      # sweep corner: D=24 (tcgen05 passes with N = 96, FMA gradient sweep)
     (130, 64, 5, 8, 32, 2),       # D=32, two j-groups, second one ragged
     (45, 72, 10, 8, 32, 3),       # D=32 on the mma gradient kernel (C >= 7): 20 pseudo-capsules, two CTA rows
+    (50, 40, 9, 8, 12, 3),        # D=12 padded to 16 on the tensor-core kernels
+    (36, 48, 8, 8, 40, 2),        # D=40 padded to 48: three pseudo-capsules, the last one half empty
 ])
 def test_against_c_oracle_fp64(capsb, dims):
     from oracle import routing_c as oc
