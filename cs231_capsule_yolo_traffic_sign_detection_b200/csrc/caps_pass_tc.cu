@@ -3,7 +3,8 @@
 // Same contract as k_pass in caps_kernels.cuh (modes A-uniform / A / L), but the K=8 prediction
 // contraction u_hat[b,i,j,:] = u[b,i,:] . W[i,j,:,:] runs on the 5th-gen tensor cores:
 //
-//   per input capsule i:   D[128 samples x (8 capsules x 16 dims)] = A_i[128 x 8] * B_i[128 x 8]^T
+//   per input capsule i:   D[128 samples x (JW capsules x DD dims)] = A_i[128 x 8] * B_i[JW*DD x 8]^T
+//   (DD, JW) = (16, 8), (24, 4), (32, 4), (48, 2): N = 128, 96, 128, 96; other D >= 9 run zero-padded to the next DD
 //
 // as three kind::tf32 MMAs (3xTF32: lo*hi + hi*lo + hi*hi; measured 1e-7 relative error, i.e.
 // fp32-grade, tools/probe_tc.cu), accumulated in TMEM.  Operands are pre-split into tf32 hi/lo
@@ -14,8 +15,8 @@
 //   producer : waits smem_empty[s], arms smem_full[s] with expect_tx, issues the two bulk copies
 //   MMA      : waits smem_full[s] and tmem_empty[t], issues 3 tcgen05.mma, commits to
 //              smem_empty[s] (operands consumed) and tmem_full[t] (accumulator ready)
-//   epilogue : warp w reads TMEM lanes 32*(w%4).. (= its 32 samples) and the 64 columns of its 4
-//              capsules with one tcgen05.ld.32x32b.x64, releases tmem_empty[t], and does the
+//   epilogue : warp w reads TMEM lanes 32*(w%4).. (= its 32 samples) and the 64 (48) columns of its JW/2
+//              capsules with one tcgen05.ld.32x32b.x64 (x32 + x16), releases tmem_empty[t], and does the
 //              per-sample part on the FMA pipe: acc += coef * u_hat (A modes) or
 //              out = u_hat . X (L mode).  lane <-> sample, exactly like the FFMA kernel.
 // Ring depths: `ns` smem stages (default 10 = 160 KB: the bulk copies have ~2000 cycles of latency to
@@ -31,18 +32,16 @@ constexpr int kTcMaxStages = 12;      // smem ring depth is a launch parameter (
 #endif
 constexpr int kTcAccumLog2 = CAPS_TC_ACCUM_LOG2;
 constexpr int kTcAccum = 1 << kTcAccumLog2;           // TMEM ring (4 x 128 columns); power of two (index = n & 3, phase = (n >> kTcAccumLog2) & 1)
-constexpr int kTcJW = 8;              // capsules per CTA  -> N = 128
-constexpr int kTcN = 128;
+constexpr int kTcN = 128;              // TMEM columns per accumulator (the MMA's N is 128 or 96, see k_pass_tc)
 constexpr int kTcABytes = 2 * 2 * 128 * 16;      // [hi/lo][kq][128 rows][16 B] = 8 KB
 constexpr int kTcBBytes = 2 * 2 * kTcN * 16;     // 8 KB
 constexpr int kTcOperandBytes = kTcABytes + kTcBBytes;       // 16 KB of MMA operands per stage
-constexpr int kTcCoefBytes = 4 * kTcJW * 32 * 4;              // kModeA: [4 lane tiles][8 capsules][32 lanes] coefficients
+constexpr int kTcCoefBytes = 4 * 8 * 32 * 4;                  // kModeA: [4 lane tiles][up to 8 capsules][32 lanes] coefficients
 __host__ __device__ constexpr int tc_stage_bytes(int mode) { return kTcOperandBytes + (mode == kModeA ? kTcCoefBytes : 0); }
-constexpr int kTcEpiWarps = 8;        // epilogue warps: 2 per TMEM lane quarter, 4 capsules (64 columns) each
+constexpr int kTcEpiWarps = 8;        // epilogue warps: 2 per TMEM lane quarter, half of the CTA's capsules each
 constexpr int kTcIssuers = 2;         // producer warps and MMA-issuer warps: each takes every kTcIssuers-th stage, because one
                                       // thread's wait -> issue chain (~250 cycles: mbarrier.try_wait alone is ~100) is longer
                                       // than the 235 cycles of tensor work it feeds
-constexpr int kTcJPW = kTcJW / (kTcEpiWarps / 4);   // capsules per epilogue warp
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 2 * kTcIssuers);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
