@@ -114,6 +114,56 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(c));
 }
+// kModeA epilogue body as ONE asm block: the probe of the NEXT stage's tmem_full barrier is issued first, the 32 packed
+// FMAs (acc += coef * u_hat on register pairs) run under its ~75-cycle round trip, and only then is the predicate read.
+// A `selp` right behind `try_wait` stalls the in-order warp (tools/probe_overlap.cu: look-ahead probing written as two
+// statements costs +100 cycles per stage; this form gains 7 %).
+__device__ __forceinline__ uint32_t fused_fma_probe(uint64_t (&A)[32], const uint64_t (&U)[32], const uint64_t (&Cf)[32],
+                                                    uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%97], %98;\n\t"
+        "fma.rn.f32x2 %0, %65, %33, %0;\n\t"
+        "fma.rn.f32x2 %1, %66, %34, %1;\n\t"
+        "fma.rn.f32x2 %2, %67, %35, %2;\n\t"
+        "fma.rn.f32x2 %3, %68, %36, %3;\n\t"
+        "fma.rn.f32x2 %4, %69, %37, %4;\n\t"
+        "fma.rn.f32x2 %5, %70, %38, %5;\n\t"
+        "fma.rn.f32x2 %6, %71, %39, %6;\n\t"
+        "fma.rn.f32x2 %7, %72, %40, %7;\n\t"
+        "fma.rn.f32x2 %8, %73, %41, %8;\n\t"
+        "fma.rn.f32x2 %9, %74, %42, %9;\n\t"
+        "fma.rn.f32x2 %10, %75, %43, %10;\n\t"
+        "fma.rn.f32x2 %11, %76, %44, %11;\n\t"
+        "fma.rn.f32x2 %12, %77, %45, %12;\n\t"
+        "fma.rn.f32x2 %13, %78, %46, %13;\n\t"
+        "fma.rn.f32x2 %14, %79, %47, %14;\n\t"
+        "fma.rn.f32x2 %15, %80, %48, %15;\n\t"
+        "fma.rn.f32x2 %16, %81, %49, %16;\n\t"
+        "fma.rn.f32x2 %17, %82, %50, %17;\n\t"
+        "fma.rn.f32x2 %18, %83, %51, %18;\n\t"
+        "fma.rn.f32x2 %19, %84, %52, %19;\n\t"
+        "fma.rn.f32x2 %20, %85, %53, %20;\n\t"
+        "fma.rn.f32x2 %21, %86, %54, %21;\n\t"
+        "fma.rn.f32x2 %22, %87, %55, %22;\n\t"
+        "fma.rn.f32x2 %23, %88, %56, %23;\n\t"
+        "fma.rn.f32x2 %24, %89, %57, %24;\n\t"
+        "fma.rn.f32x2 %25, %90, %58, %25;\n\t"
+        "fma.rn.f32x2 %26, %91, %59, %26;\n\t"
+        "fma.rn.f32x2 %27, %92, %60, %27;\n\t"
+        "fma.rn.f32x2 %28, %93, %61, %28;\n\t"
+        "fma.rn.f32x2 %29, %94, %62, %29;\n\t"
+        "fma.rn.f32x2 %30, %95, %63, %30;\n\t"
+        "fma.rn.f32x2 %31, %96, %64, %31;\n\t"
+        "selp.u32 %32, 1, 0, p;\n\t}"
+        : "+l"(A[0]), "+l"(A[1]), "+l"(A[2]), "+l"(A[3]), "+l"(A[4]), "+l"(A[5]), "+l"(A[6]), "+l"(A[7]), "+l"(A[8]), "+l"(A[9]), "+l"(A[10]), "+l"(A[11]), "+l"(A[12]), "+l"(A[13]), "+l"(A[14]), "+l"(A[15]), "+l"(A[16]), "+l"(A[17]), "+l"(A[18]), "+l"(A[19]), "+l"(A[20]), "+l"(A[21]), "+l"(A[22]), "+l"(A[23]), "+l"(A[24]), "+l"(A[25]), "+l"(A[26]), "+l"(A[27]), "+l"(A[28]), "+l"(A[29]), "+l"(A[30]), "+l"(A[31]), "=r"(ok)
+        : "l"(U[0]), "l"(U[1]), "l"(U[2]), "l"(U[3]), "l"(U[4]), "l"(U[5]), "l"(U[6]), "l"(U[7]), "l"(U[8]), "l"(U[9]), "l"(U[10]), "l"(U[11]), "l"(U[12]), "l"(U[13]), "l"(U[14]), "l"(U[15]), "l"(U[16]), "l"(U[17]), "l"(U[18]), "l"(U[19]), "l"(U[20]), "l"(U[21]), "l"(U[22]), "l"(U[23]), "l"(U[24]), "l"(U[25]), "l"(U[26]), "l"(U[27]), "l"(U[28]), "l"(U[29]), "l"(U[30]), "l"(U[31]),
+          "l"(Cf[0]), "l"(Cf[1]), "l"(Cf[2]), "l"(Cf[3]), "l"(Cf[4]), "l"(Cf[5]), "l"(Cf[6]), "l"(Cf[7]), "l"(Cf[8]), "l"(Cf[9]), "l"(Cf[10]), "l"(Cf[11]), "l"(Cf[12]), "l"(Cf[13]), "l"(Cf[14]), "l"(Cf[15]), "l"(Cf[16]), "l"(Cf[17]), "l"(Cf[18]), "l"(Cf[19]), "l"(Cf[20]), "l"(Cf[21]), "l"(Cf[22]), "l"(Cf[23]), "l"(Cf[24]), "l"(Cf[25]), "l"(Cf[26]), "l"(Cf[27]), "l"(Cf[28]), "l"(Cf[29]), "l"(Cf[30]), "l"(Cf[31]), "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -425,7 +475,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 #pragma unroll
                     for (int d = 0; d < DD; ++d) acc[jj][d] = uh[jj * DD + d];
             }
-        } else
+        } else {
+        bool ready = false;                  // kModeA: tmem_full of this stage was already seen complete by the previous one
         for (int n = 0; n < n_i; ++n) {
             // Every epilogue warp handles every stage, so the stage rate is bounded by this loop's serial chain of fixed
             // latencies (tools/probe_overlap.cu: a try_wait round trip is ~75 cycles even on a completed mbarrier, LDS
@@ -437,7 +488,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
             float cc[JPW];
 #pragma unroll
             for (int jj = 0; jj < JPW; ++jj) cc[jj] = 0.f;
-            mbar_wait(tmem_full + 8 * t, (n >> kTcAccumLog2) & 1);
+            if (!ready) mbar_wait(tmem_full + 8 * t, (n >> kTcAccumLog2) & 1);
+            ready = false;
             if (MODE == kModeA && tvalid) {
                 const uint32_t ca = stages + (uint32_t)s * kTcStageBytes + coef_off;
 #pragma unroll
@@ -463,6 +515,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                     const float dot = (d0 + d1) + (d2 + d3);
                     if (tvalid && j0 + jj < p.C && !(p.dbg & 1)) p.out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = dot;
                 }
+            } else if (NC == 64 && MODE == kModeA) {
+                uint64_t A2[32], U2[32], C2[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int jj = (2 * e) / DD, d = (2 * e) % DD;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(A2[e]) : "f"(acc[jj][d]), "f"(acc[jj][d + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(U2[e]) : "f"(uh[2 * e]), "f"(uh[2 * e + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(C2[e]) : "f"(cc[jj]), "f"(cc[jj]));
+                }
+                const int n1 = n + 1 < n_i ? n + 1 : n;          // last stage: a harmless probe of the own (complete) barrier
+                ready = fused_fma_probe(A2, U2, C2, tmem_full + 8 * (n1 & (kTcAccum - 1)), (n1 >> kTcAccumLog2) & 1) != 0 &&
+                        n + 1 < n_i;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int jj = (2 * e) / DD, d = (2 * e) % DD;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[jj][d]), "=f"(acc[jj][d + 1]) : "l"(A2[e]));
+                }
             } else {
 #pragma unroll
                 for (int jj = 0; jj < JPW; ++jj) {
@@ -477,6 +546,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
                 if (lane == 0) mbar_arrive(smem_empty + 8 * s);
                 if (++s == ns) { s = 0; sph ^= 1; }
             }
+        }
         }
         if (MODE != kModeL && tvalid) {
 #pragma unroll
