@@ -164,6 +164,53 @@ __device__ __forceinline__ uint32_t fused_fma_probe(uint64_t (&A)[32], const uin
     return ok;
 }
 
+// kModeL counterpart: 8 packed partial sums, pair e of the 64 columns goes to partial e / 4 (8 consecutive dims each)
+__device__ __forceinline__ uint32_t fused_dot_probe(uint64_t (&Dp)[8], const uint64_t (&U)[32], const uint64_t (&X)[32],
+                                                    uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%73], %74;\n\t"
+        "fma.rn.f32x2 %0, %9, %41, %0;\n\t"
+        "fma.rn.f32x2 %0, %10, %42, %0;\n\t"
+        "fma.rn.f32x2 %0, %11, %43, %0;\n\t"
+        "fma.rn.f32x2 %0, %12, %44, %0;\n\t"
+        "fma.rn.f32x2 %1, %13, %45, %1;\n\t"
+        "fma.rn.f32x2 %1, %14, %46, %1;\n\t"
+        "fma.rn.f32x2 %1, %15, %47, %1;\n\t"
+        "fma.rn.f32x2 %1, %16, %48, %1;\n\t"
+        "fma.rn.f32x2 %2, %17, %49, %2;\n\t"
+        "fma.rn.f32x2 %2, %18, %50, %2;\n\t"
+        "fma.rn.f32x2 %2, %19, %51, %2;\n\t"
+        "fma.rn.f32x2 %2, %20, %52, %2;\n\t"
+        "fma.rn.f32x2 %3, %21, %53, %3;\n\t"
+        "fma.rn.f32x2 %3, %22, %54, %3;\n\t"
+        "fma.rn.f32x2 %3, %23, %55, %3;\n\t"
+        "fma.rn.f32x2 %3, %24, %56, %3;\n\t"
+        "fma.rn.f32x2 %4, %25, %57, %4;\n\t"
+        "fma.rn.f32x2 %4, %26, %58, %4;\n\t"
+        "fma.rn.f32x2 %4, %27, %59, %4;\n\t"
+        "fma.rn.f32x2 %4, %28, %60, %4;\n\t"
+        "fma.rn.f32x2 %5, %29, %61, %5;\n\t"
+        "fma.rn.f32x2 %5, %30, %62, %5;\n\t"
+        "fma.rn.f32x2 %5, %31, %63, %5;\n\t"
+        "fma.rn.f32x2 %5, %32, %64, %5;\n\t"
+        "fma.rn.f32x2 %6, %33, %65, %6;\n\t"
+        "fma.rn.f32x2 %6, %34, %66, %6;\n\t"
+        "fma.rn.f32x2 %6, %35, %67, %6;\n\t"
+        "fma.rn.f32x2 %6, %36, %68, %6;\n\t"
+        "fma.rn.f32x2 %7, %37, %69, %7;\n\t"
+        "fma.rn.f32x2 %7, %38, %70, %7;\n\t"
+        "fma.rn.f32x2 %7, %39, %71, %7;\n\t"
+        "fma.rn.f32x2 %7, %40, %72, %7;\n\t"
+        "selp.u32 %8, 1, 0, p;\n\t}"
+        : "+l"(Dp[0]), "+l"(Dp[1]), "+l"(Dp[2]), "+l"(Dp[3]), "+l"(Dp[4]), "+l"(Dp[5]), "+l"(Dp[6]), "+l"(Dp[7]), "=r"(ok)
+        : "l"(U[0]), "l"(U[1]), "l"(U[2]), "l"(U[3]), "l"(U[4]), "l"(U[5]), "l"(U[6]), "l"(U[7]), "l"(U[8]), "l"(U[9]), "l"(U[10]), "l"(U[11]), "l"(U[12]), "l"(U[13]), "l"(U[14]), "l"(U[15]), "l"(U[16]), "l"(U[17]), "l"(U[18]), "l"(U[19]), "l"(U[20]), "l"(U[21]), "l"(U[22]), "l"(U[23]), "l"(U[24]), "l"(U[25]), "l"(U[26]), "l"(U[27]), "l"(U[28]), "l"(U[29]), "l"(U[30]), "l"(U[31]),
+          "l"(X[0]), "l"(X[1]), "l"(X[2]), "l"(X[3]), "l"(X[4]), "l"(X[5]), "l"(X[6]), "l"(X[7]), "l"(X[8]), "l"(X[9]), "l"(X[10]), "l"(X[11]), "l"(X[12]), "l"(X[13]), "l"(X[14]), "l"(X[15]), "l"(X[16]), "l"(X[17]), "l"(X[18]), "l"(X[19]), "l"(X[20]), "l"(X[21]), "l"(X[22]), "l"(X[23]), "l"(X[24]), "l"(X[25]), "l"(X[26]), "l"(X[27]), "l"(X[28]), "l"(X[29]), "l"(X[30]), "l"(X[31]), "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -502,7 +549,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * t);  // accumulator t may be overwritten
-            if (MODE == kModeL) {
+            if (MODE == kModeL && NC == 64) {
+                uint64_t U2[32], X2[32], D2[8];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int jj = (2 * e) / DD, d = (2 * e) % DD;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(U2[e]) : "f"(uh[2 * e]), "f"(uh[2 * e + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(X2[e]) : "f"(acc[jj][d]), "f"(acc[jj][d + 1]));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) D2[k] = 0ull;
+                const int n1 = n + 1 < n_i ? n + 1 : n;
+                ready = fused_dot_probe(D2, U2, X2, tmem_full + 8 * (n1 & (kTcAccum - 1)), (n1 >> kTcAccumLog2) & 1) != 0 && n + 1 < n_i;
+                float part[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    float lo, hi;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(D2[k]));
+                    part[k] = lo + hi;
+                }
+                constexpr int GPC = 8 / JPW;                      // partial sums per capsule (2 or 4)
+#pragma unroll
+                for (int jj = 0; jj < JPW; ++jj) {
+                    float dot = part[jj * GPC];
+#pragma unroll
+                    for (int k = 1; k < GPC; ++k) dot += part[jj * GPC + k];
+                    if (tvalid && j0 + jj < p.C && !(p.dbg & 1)) p.out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = dot;
+                }
+            } else if (MODE == kModeL) {
 #pragma unroll
                 for (int jj = 0; jj < JPW; ++jj) {
                     // four partial sums in two FFMA2 chains (half the FMA instructions, chains of DD/4 instead of DD)
