@@ -2,7 +2,9 @@
  *
  * This is the drop-in boundary for ONE path of Cranial-XIX/cs231-capsule-yolo-traffic-sign-detection:
  * the caps->caps branch of `CapsuleLayer` (reference models.py:46-83) plus the margin-loss
- * gradient that feeds it (reference loss_fns.py:11-23, models.py:117).  The reference has no
+ * gradient that feeds it (reference loss_fns.py:11-23, models.py:117); since ABI version 2 also the
+ * steps directly before and after that branch (caps_primary_squash, caps_dark_regroup,
+ * caps_dark_loss: reference models.py:81-82, :393-399, loss_fns.py:187-204).  The reference has no
  * FFI of its own -- its boundary is the Python class -- so these entry points are what a ctypes
  * binding behind that class calls (the in-repo binding is
  * cs231_capsule_yolo_traffic_sign_detection_b200/_cabi.py).
