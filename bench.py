@@ -324,6 +324,21 @@ def main_gpu(args, rank, world, device):
                                     'the tcgen05 path beats what any fp32-FMA kernel could do',
                      'share_of_step': ms_pass / ms_prof,
                      'hbm_gbs': pass_bytes / (ms_pass / max(n_pass, 1) * 1e-3) / 1e9}
+    # the HBM-bound kernels of the step: softmax forward (one [B,N,C] array read + written, R-1 launches) and
+    # softmax backward (c, dc [, beta carry] read, beta written: 3 arrays for the last iteration, 4 for the others)
+    roofline_softmax = None
+    try:
+        Re = 1 if C == 1 else R
+        n_arrays = 2 * (Re - 1) + 3 * (Re - 1) + max(Re - 2, 0)
+        if n_cls[5] and n_arrays:
+            sm_bytes = n_arrays * 4.0 * B * N * C                      # per step
+            sm_gbs = sm_bytes / (ms_cls[5] / args.steps * 1e-3) / 1e9
+            roofline_softmax = {'bound': 'hbm', 'kernel': 'k_softmax_reg + k_softmax_bwd_staged; %d launches/step' % (n_cls[5] // args.steps),
+                                'achieved': sm_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': sm_gbs / hbm_peak,
+                                'peak_source': hbm_src + ' (a copy bandwidth: read-mostly kernels can exceed it)',
+                                'share_of_step': ms_cls[5] / ms_prof}
+    except Exception:
+        roofline_softmax = None
     step_tf = flops_per_sample() * B / (ms_per_step * 1e-3) / 1e12
     step_gbs = hbm_bytes_per_step(B) / (ms_per_step * 1e-3) / 1e9
     roofline_step = {'algorithmic_tflops': step_tf, 'frac_of_fp32_peak': step_tf / fma_peak,
@@ -345,7 +360,7 @@ def main_gpu(args, rank, world, device):
                 'api': 'caps_route_step_host (pinned host u,y -> device; loss -> host)'},
         'gpu_launches': int(launches),
         'clocks': clk,
-        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'roofline_step': roofline_step,
+        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'roofline_softmax': roofline_softmax, 'roofline_step': roofline_step,
         'kernel_ms_per_step': per_class, 'profiled_ms_per_step': ms_prof / args.steps,
         'cpu_baseline': cpu,
     }
