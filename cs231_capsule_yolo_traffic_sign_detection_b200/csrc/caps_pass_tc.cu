@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
 
     if (warp >= kTcEpiWarps && warp < kTcEpiWarps + kTcIssuers) {
         // ===== producer: converged warp, one elected lane arms the barrier and issues both copies =====
-        // producer w takes stages n = w, w + NI, w + 2 NI, ...  (uniform mode: a single producer)
-        constexpr int NI = (MODE == kModeAUniform) ? 1 : kTcIssuers;
+        // producer w takes stages n = w, w + NI, w + 2 NI, ...
+        constexpr int NI = kTcIssuers;
         const int w = warp - kTcEpiWarps;
         if (w >= NI) goto role_done;
         const float* asrc = p.ua + ((size_t)tq * p.N + i_begin + w) * 2048;
@@ -459,15 +459,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
         // descriptors differ between stages only in the 14-bit start-address field (bytes >> 4)
         const uint64_t desc0 = umma_desc(stages, 2048, 128);
         // issuer w takes stages n = w, w + NI, ...: stages are independent (own smem slot, own accumulator), and a
-        // tcgen05.commit only tracks the MMAs of the thread that executes it.  Uniform mode is one dependent
-        // accumulation chain, so it keeps a single issuer.
-        constexpr int NI = (MODE == kModeAUniform) ? 1 : kTcIssuers;
+        // tcgen05.commit only tracks the MMAs of the thread that executes it.  Uniform mode: one dependent accumulation
+        // chain per issuer, each in its own accumulator (a single issuer's wait -> issue chain took 312 cycles per stage).
+        constexpr int NI = kTcIssuers;
         const int w = warp - kTcEpiWarps - kTcIssuers;
         if (w >= NI) goto role_done;
         int s = w;
         uint32_t sph = 0;
         for (int n = w; n < n_i; n += NI) {
-            const int t = (MODE == kModeAUniform) ? 0 : (n & (kTcAccum - 1));
+            // uniform mode: issuer w accumulates ITS stages (n = w, w + 2, ...) in accumulator w; the epilogue adds the two
+            const int t = (MODE == kModeAUniform) ? w : (n & (kTcAccum - 1));
             if (MODE != kModeAUniform) mbar_wait(tmem_empty + 8 * t, ((n >> kTcAccumLog2) & 1) ^ 1);
             mbar_wait(smem_full + 8 * s, sph);
             tc_fence_after();
@@ -476,7 +477,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
             if (MODE == kModeAUniform)
                 // uniform couplings: sum_i u_hat_i IS one long GEMM over (i,k): accumulate in TMEM across all the
                 // stages, signal the epilogue once
-                umma_stage(tmem_base, a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full, n > 0, n == n_i - 1);
+                umma_stage(tmem_base + (uint32_t)(t * kTcN), a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full + 8 * t,
+                           n >= NI, n + NI >= n_i);
             else
                 umma_stage(tmem_base + (uint32_t)(t * kTcN), a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full + 8 * t);
             s += NI;
@@ -512,16 +514,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pass_tc(PassTcParams p) {
         int s = 0;
         uint32_t sph = 0;
         if (MODE == kModeAUniform) {
-            if (n_i > 0) {
-                mbar_wait(tmem_full, 0);
-                tc_fence_after();
-                float uh[NC];
-                tmem_ld<NC>(lane_base, uh);
+            // one accumulator per issuer warp (each a dependent chain of its own stages): summed here, in fixed order
 #pragma unroll
-                for (int jj = 0; jj < JPW; ++jj)
+            for (int w = 0; w < kTcIssuers; ++w)
+                if (n_i > w) {
+                    mbar_wait(tmem_full + 8 * w, 0);
+                    tc_fence_after();
+                    float uh[NC];
+                    tmem_ld<NC>(lane_base + (uint32_t)(w * kTcN), uh);
 #pragma unroll
-                    for (int d = 0; d < DD; ++d) acc[jj][d] = uh[jj * DD + d];
-            }
+                    for (int jj = 0; jj < JPW; ++jj)
+#pragma unroll
+                        for (int d = 0; d < DD; ++d) acc[jj][d] += uh[jj * DD + d];
+                }
         } else {
         bool ready = false;                  // kModeA: tmem_full of this stage was already seen complete by the previous one
         for (int n = 0; n < n_i; ++n) {
