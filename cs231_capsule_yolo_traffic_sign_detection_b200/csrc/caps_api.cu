@@ -7,10 +7,25 @@
 // caller's workspace is carved deterministically from the dims).
 #include "caps_internal.h"
 
+#include <algorithm>
 #include <atomic>
+#include <mutex>
 
 namespace caps {
 thread_local char g_err[512] = "";
+int ensure_dyn_smem(const void* func, size_t smem, SmemAttrCache& cache) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) {            // beyond the cache: set unconditionally (cheap, just not free)
+        CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    }
+    if (smem > cache.bytes[dev].load(std::memory_order_relaxed)) {
+        CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cache.bytes[dev].store(smem, std::memory_order_relaxed);      // racing threads both set it: idempotent
+    }
+    return 0;
+}
 int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -30,9 +45,41 @@ int g_tune_gradmma = 1;  // 1 = mma.sync gradient kernel where it applies (D == 
 int g_tune_hostmb = 0;   // caps_route_step_host: 0 = auto (3 micro-batches from B >= 2048), 1 = single batch
 int g_tune_sbstaged = 1;  // softmax backward through the staged kernel (16 < C <= 48)
 int g_tune_tc = 1;       // 1 = use the tcgen05 pass kernel where it applies, 0 = FFMA kernel only
+int g_tune_fused = 1;    // 1 = cluster-fused sweep (logits -> softmax -> weighted sum in one kernel) where it applies
+
+// ---- forward records ---------------------------------------------------------------------------
+// caps_route_forward notes, per (device, workspace pointer), the dims it ran with and the engines it used (which
+// operand copies the workspace now holds); caps_route_backward looks the record up, returns CAPS_E_STATE when there
+// is none / the dims differ / the forward ran without with_grad, and replays the recorded engine choices instead of
+// reading the tuning knobs again.  Host-side bookkeeping only (mutex-guarded, fixed size, oldest entry recycled).
+struct FwdRecord { const void* ws; int dev, B, N, C, K, D, R; bool with_grad, use_tc, fused; unsigned long stamp; };
+constexpr int kFwdRecords = 256;
+FwdRecord g_records[kFwdRecords];
+unsigned long g_record_clock = 0;
+std::mutex g_record_mu;
+
+void record_forward(const void* ws, const Plan& pl) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_record_mu);
+    int slot = 0;
+    for (int e = 0; e < kFwdRecords; ++e) {
+        if (g_records[e].ws == ws && g_records[e].dev == dev) { slot = e; break; }
+        if (g_records[e].stamp < g_records[slot].stamp) slot = e;
+    }
+    g_records[slot] = FwdRecord{ws, dev, pl.B, pl.N, pl.C, pl.K, pl.D, pl.R, pl.with_grad, pl.use_tc, pl.fused, ++g_record_clock};
+}
+bool lookup_forward(const void* ws, FwdRecord& out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_record_mu);
+    for (int e = 0; e < kFwdRecords; ++e)
+        if (g_records[e].stamp != 0 && g_records[e].ws == ws && g_records[e].dev == dev) { out = g_records[e]; return true; }
+    return false;
+}
 
 // ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
-enum KClass { kcLayout = 0, kcPassA0, kcPassL, kcPassA, kcSquash, kcSoftmax, kcGrad, kcReduceDu, kcLoss, kcOther, kcCount };
+enum KClass { kcLayout = 0, kcPassA0, kcPassL, kcPassA, kcSquash, kcSoftmax, kcGrad, kcReduceDu, kcLoss, kcOther, kcFused, kcCount };
 std::atomic<long> g_launches{0};
 int g_prof_on = 0;
 constexpr int kProfPool = 8192;
@@ -82,7 +129,9 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.SPT = spt;
     p.ntg = cdiv(p.nbt, p.SPT);
     // tc_jw(DP) capsules per tcgen05 CTA; D < DP (21 -> 24, 9..15 -> 16, ...) runs on the zero-padded W copy
-    p.use_tc = g_tune_tc != 0 && p.DP >= 16 && C >= 2 && (p.DP != 16 || C >= 4);
+    p.tc_ok = p.DP >= 16 && C >= 2 && (p.DP != 16 || C >= 4);      // shape is eligible: sizes the layout
+    p.use_tc = g_tune_tc != 0 && p.tc_ok;                          // engine choice: a knob
+    p.fused = g_tune_fused != 0 && fused_supported(p);
     // split the i range until the grid fills the machine: the FMA kernel wants ~4 CTAs per SM, the tcgen05
     // kernel owns an SM (all of TMEM), so one wave of its CTAs (128-sample quads x 8-capsule groups) is enough
     const long ctas = p.use_tc ? (long)cdiv(C, tc_jw(p.DP)) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
@@ -90,7 +139,7 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     if (g_tune_isplit <= 0 && p.use_tc) {
         // smallest split count (<= 32) whose grid wastes the least of its last wave of 148 CTAs
         double best = -1.0;
-        for (int cand = 1; cand <= 32; ++cand) {
+        for (int cand = 1; cand <= kMaxSplits; ++cand) {
             const long grid = ctas * cand;
             const double eff = (double)grid / (double)(((grid + 147) / 148) * 148);
             if (eff > best + 0.05) { best = eff; is = cand; }
@@ -98,22 +147,24 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     }
     const int max_is = cdiv(N, kPassIC);
     if (is > max_is) is = max_is;
-    if (is > 64) is = 64;
+    if (is > kMaxSplits) is = kMaxSplits;
     if (is < 1) is = 1;
     p.i_per_split = cdiv(cdiv(N, is), kPassIC) * kPassIC;
     p.IS = cdiv(N, p.i_per_split);
     p.xs = round64((size_t)p.nbt * C * p.DP * 32);
     p.cs = round64((size_t)p.nbt * N * C * 32);
     p.us = round64((size_t)p.nbt * N * K * 32);
+    // ---- layout: depends on (dims, with_grad) only -------------------------------------------------------------
+    const int part_slots = std::min(kMaxSplits, max_is);
     size_t o = 0;
-    p.o_ua = o; o += p.use_tc ? round64(tc_ua_floats(B, N)) : 0;
-    p.o_wb = o; o += p.use_tc ? round64(tc_wb_floats(N, C, p.DP)) : 0;
+    p.o_ua = o; o += p.tc_ok ? round64(tc_ua_floats(B, N)) : 0;
+    p.o_wb = o; o += p.tc_ok ? round64(tc_wb_floats(N, C, p.DP)) : 0;
     p.o_ut = o; o += p.us;
     p.o_wp = o; o += p.pad_w ? round64((size_t)N * C * K * p.DP) : 0;
     p.o_vsum = o; o += p.xs;
     p.o_s = o; o += p.xs * p.Reff;
     p.o_v = o; o += p.xs * p.Reff;
-    p.o_part = o; o += p.xs * p.IS;
+    p.o_part = o; o += p.xs * part_slots;
     p.o_c = o; o += p.cs * (p.with_grad ? (p.Reff > 1 ? p.Reff - 1 : 0) : (p.Reff > 1 ? 1 : 0));
     p.o_beta = o; o += p.with_grad ? p.cs * (p.Reff > 1 ? p.Reff - 1 : 0) : 0;
     p.o_tmp = o; o += p.with_grad && p.Reff > 1 ? p.cs : 0;
@@ -132,21 +183,21 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
         case 48: { constexpr int DP_ = 48; CALL; } break; \
     }
 
-int launch_squash(const Plan& pl, const float* part, float scale, float* s_out, float* v_out, float* vsum,
+int launch_squash(const Plan& pl, const float* part, int IS, float scale, float* s_out, float* v_out, float* vsum,
                   int accumulate, float* v_pub, cudaStream_t st) {
     const long n = (long)pl.nbt * pl.C * 32;
     LaunchScope ls_(kcSquash, st);
-    DISPATCH_DP(pl, (k_squash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, pl.IS, pl.xs, scale, s_out, v_out, vsum,
+    DISPATCH_DP(pl, (k_squash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, IS, pl.xs, scale, s_out, v_out, vsum,
                                                                   accumulate, v_pub, pl.B, pl.C, pl.D, pl.nbt)));
     LAUNCH_CHECK();
     return 0;
 }
 
-int launch_dsquash(const Plan& pl, const float* part, const float* grad_v, const int64_t* y, float mscale,
+int launch_dsquash(const Plan& pl, const float* part, int IS, const float* grad_v, const int64_t* y, float mscale,
                    const float* lgrad, const float* v_last, const float* s_in, float* ds_out, float out_scale, cudaStream_t st) {
     const long n = (long)pl.nbt * pl.C * 32;
     LaunchScope ls_(kcSquash, st);
-    DISPATCH_DP(pl, (k_dsquash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, pl.IS, pl.xs, grad_v, y, mscale, lgrad, v_last,
+    DISPATCH_DP(pl, (k_dsquash<DP_><<<cdiv(n, 128), 128, 0, st>>>(part, IS, pl.xs, grad_v, y, mscale, lgrad, v_last,
                                                                    s_in, ds_out, out_scale, pl.B, pl.C, pl.D, pl.nbt)));
     LAUNCH_CHECK();
     return 0;
@@ -229,8 +280,9 @@ int caps_set_tuning(const char* name, int value) {
     if (!strcmp(name, "sbstaged")) { g_tune_sbstaged = value != 0; return 0; }
     if (!strcmp(name, "hostmb")) { g_tune_hostmb = value; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
+    if (!strcmp(name, "fused")) { g_tune_fused = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
-        if (value < 0 || value > 64) return fail(CAPS_E_BADARG, "isplit must be in [0,64]");
+        if (value < 0 || value > kMaxSplits) return fail(CAPS_E_BADARG, "isplit must be in [0,%d]", kMaxSplits);
         g_tune_isplit = value;
         return 0;
     }
@@ -260,54 +312,71 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
     float* w = static_cast<float*>(ws);
     float* ut = w + pl.o_ut;
     const float* Wp = W;
+    int rc;
     if (pl.pad_w) {
         const long rows = (long)N * C * K;
         { LaunchScope ls_(kcLayout, st); k_pad_w<<<cdiv(rows * pl.DP, 256), 256, 0, st>>>(W, w + pl.o_wp, rows, D, pl.DP); }
         LAUNCH_CHECK();
         Wp = w + pl.o_wp;
     }
-    {
+    if (pl.use_tc) {
+        // one pass over u writes the tcgen05 operand copy (tf32 hi/lo) and, when someone will read it (the gradient
+        // kernels), the lane-tile copy
+        { LaunchScope ls_(kcLayout, st); rc = launch_prep_u_tc(pl, u, w + pl.o_ua, pl.with_grad ? ut : nullptr, st); }
+        if (rc) return rc;
+        { LaunchScope ls_(kcLayout, st); rc = launch_prep_w_tc(pl, Wp, w + pl.o_wb, st); }
+        if (rc) return rc;
+    } else {
         const long n = (long)pl.nbt * N * 32;
         { LaunchScope ls_(kcLayout, st); k_prep_u<8><<<cdiv(n, 256), 256, 0, st>>>(u, ut, B, N, pl.nbt); }
         LAUNCH_CHECK();
     }
-    if (pl.use_tc) {
-        int rc;
-        { LaunchScope ls_(kcLayout, st); rc = launch_prep_u_tc(pl, u, w + pl.o_ua, st); }
-        if (rc) return rc;
-        { LaunchScope ls_(kcLayout, st); rc = launch_prep_w_tc(pl, Wp, w + pl.o_wb, st); }
-        if (rc) return rc;
-    }
+    record_forward(ws, pl);
     float* vsum = w + pl.o_vsum;
     float* part = w + pl.o_part;
+    const int ISf = pl.fused ? fused_pick_splits(pl, false, g_tune_isplit) : 0;
     for (int r = 0; r < pl.Reff; ++r) {
         float* s_r = w + pl.o_s + pl.xs * r;
         float* v_r = w + pl.o_v + pl.xs * r;
         const bool last = (r == pl.Reff - 1);
         PassParams pp{};
         pp.ut = ut; pp.W = Wp; pp.N = N; pp.C = C; pp.nbt = pl.nbt; pp.i_per_split = pl.i_per_split;
-        int rc;
         if (r == 0) {
             pp.out = part;
             if ((rc = run_pass(pl, kModeAUniform, pp, w, st))) return rc;
-            if ((rc = launch_squash(pl, part, 1.f / (float)C, s_r, v_r, vsum, 0, last ? v : nullptr, st))) return rc;
-        } else {
-            float* c_r = w + pl.o_c + (pl.with_grad ? pl.cs * (r - 1) : 0);
-            pp.X = vsum; pp.out = c_r;
-            if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
-            const long n = (long)pl.nbt * N * 32;
-            {
-                LaunchScope ls_(kcSoftmax, st);
-                float* cp = last ? c_out : nullptr;
-                if (C <= 16) k_softmax_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
-                else if (C <= 48) k_softmax_reg<48><<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
-                else k_softmax<<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
-            }
-            LAUNCH_CHECK();
-            pp.X = nullptr; pp.coef = c_r; pp.out = part;
-            if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
-            if ((rc = launch_squash(pl, part, 1.f, s_r, v_r, vsum, 1, last ? v : nullptr, st))) return rc;
+            if ((rc = launch_squash(pl, part, pl.IS, 1.f / (float)C, s_r, v_r, vsum, 0, last ? v : nullptr, st))) return rc;
+            continue;
         }
+        float* c_r = w + pl.o_c + (pl.with_grad ? pl.cs * (r - 1) : 0);
+        if (pl.fused) {
+            // logits -> softmax -> weighted sum in ONE sweep; c^r is written once, only if somebody will read it
+            const bool want_c = pl.with_grad || (last && c_out != nullptr);
+            {
+                LaunchScope ls_(kcFused, st);
+                rc = launch_sweep_fused(pl, false, w + pl.o_ua, w + pl.o_wb, vsum, nullptr, nullptr, want_c ? c_r : nullptr, part, ISf, st);
+            }
+            if (rc) return rc;
+            if ((rc = launch_squash(pl, part, ISf, 1.f, s_r, v_r, vsum, 1, last ? v : nullptr, st))) return rc;
+            if (last && c_out != nullptr) {
+                LaunchScope ls_(kcOther, st);
+                if ((rc = launch_coef_public(pl, c_r, c_out, st))) return rc;
+            }
+            continue;
+        }
+        pp.X = vsum; pp.out = c_r;
+        if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
+        const long n = (long)pl.nbt * N * 32;
+        {
+            LaunchScope ls_(kcSoftmax, st);
+            float* cp = last ? c_out : nullptr;
+            if (C <= 16) k_softmax_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
+            else if (C <= 48) k_softmax_reg<48><<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
+            else k_softmax<<<cdiv(n, 128), 128, 0, st>>>(c_r, cp, B, N, C, pl.nbt);
+        }
+        LAUNCH_CHECK();
+        pp.X = nullptr; pp.coef = c_r; pp.out = part;
+        if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
+        if ((rc = launch_squash(pl, part, pl.IS, 1.f, s_r, v_r, vsum, 1, last ? v : nullptr, st))) return rc;
     }
     if (c_out != nullptr && pl.Reff == 1) {      // R == 1 or C == 1: the couplings are the constant 1/C
         const long n = (long)B * N * C;
@@ -335,6 +404,19 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         return fail(CAPS_E_BADARG, "caps_route_backward: W, dW, du and ws must be 16-byte aligned");
     if (ws_bytes < pl.total * sizeof(float))
         return fail(CAPS_E_WORKSPACE, "caps_route_backward: workspace %zu < %zu bytes", ws_bytes, pl.total * sizeof(float));
+    {
+        // the forward that filled this workspace: its dims must be ours, and its engine choices (not the knobs as
+        // they stand now) say which operand copies the workspace holds
+        FwdRecord rec;
+        if (!lookup_forward(ws, rec))
+            return fail(CAPS_E_STATE, "caps_route_backward: no caps_route_forward has filled this workspace");
+        if (rec.B != B || rec.N != N || rec.C != C || rec.K != K || rec.D != D || rec.R != R)
+            return fail(CAPS_E_STATE, "caps_route_backward: workspace was filled for B=%d N=%d C=%d K=%d D=%d R=%d, not B=%d N=%d C=%d K=%d D=%d R=%d",
+                        rec.B, rec.N, rec.C, rec.K, rec.D, rec.R, B, N, C, K, D, R);
+        if (!rec.with_grad) return fail(CAPS_E_STATE, "caps_route_backward: the forward ran with with_grad = 0 (no saved state)");
+        pl.use_tc = rec.use_tc;
+        pl.fused = rec.fused;
+    }
     float* w = static_cast<float*>(ws);
     const float* ut = w + pl.o_ut;
     const float* Wp = pl.pad_w ? w + pl.o_wp : W;
@@ -346,39 +428,45 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     // reader); the FMA kernel multiplies by cconst[0] itself.  Same fp32 product either way.
     const bool grad_mma = g_tune_gradmma && pl.DP >= 16 && pl.JW == 8;       // D >= 9, C >= 7
     const float ds0_scale = grad_mma ? 1.f / (float)C : 1.f;
+    const int ISb = pl.fused ? fused_pick_splits(pl, true, g_tune_isplit) : pl.IS;
     // top: dv = grad_v + margin gradient ; ds^{R-1}
-    if ((rc = launch_dsquash(pl, nullptr, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),
+    if ((rc = launch_dsquash(pl, nullptr, 0, grad_v, y, margin_scale, loss_grad_dev, w + pl.o_v + pl.xs * (Re - 1),
                              w + pl.o_s + pl.xs * (Re - 1), w + pl.o_ds + pl.xs * (Re - 1), Re == 1 ? ds0_scale : 1.f, st)))
         return rc;
     for (int r = Re - 1; r >= 1; --r) {
         const float* c_r = w + pl.o_c + pl.cs * (r - 1);
         float* beta_r = w + pl.o_beta + pl.cs * (r - 1);
         const float* beta_next = (r == Re - 1) ? nullptr : w + pl.o_beta + pl.cs * r;
-        PassParams pp{};
-        pp.ut = ut; pp.W = Wp; pp.N = N; pp.C = C; pp.nbt = pl.nbt; pp.i_per_split = pl.i_per_split;
-        pp.X = w + pl.o_ds + pl.xs * r; pp.out = tmp;                       // dc = u_hat . ds^r
-        if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
-        const long n = (long)pl.nbt * N * 32;
-        {
-            LaunchScope ls_(kcSoftmax, st);
-            // the register-resident variant (114 registers) loses to the three-pass one here: the second and
-            // third passes hit L1, and occupancy matters more than the re-reads (measured 1.9 vs 1.0 ms)
-            if (C <= 16) k_softmax_bwd_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
-            else if (C <= 48 && g_tune_sbstaged) {
-                const size_t smem = (size_t)4 * 2 * C * 32 * sizeof(float);
-                static size_t attr_set = 0;
-                if (smem > attr_set) {
-                    CUDA_TRY(cudaFuncSetAttribute(k_softmax_bwd_staged<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_set = smem;
-                }
-                const long nblocks = (long)pl.nbt * N;
-                k_softmax_bwd_staged<48><<<cdiv(nblocks, 4), 128, smem, st>>>(c_r, tmp, beta_next, beta_r, C, nblocks);
-            } else k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+        if (pl.fused) {
+            // dc = u_hat . ds^r ; beta^r = beta^{r+1} + c^r (dc - sum_j c^r dc) ; dv^{r-1} = sum_i beta^r u_hat : one sweep
+            {
+                LaunchScope ls_(kcFused, st);
+                rc = launch_sweep_fused(pl, true, w + pl.o_ua, w + pl.o_wb, w + pl.o_ds + pl.xs * r, c_r, beta_next, beta_r, part, ISb, st);
+            }
+            if (rc) return rc;
+        } else {
+            PassParams pp{};
+            pp.ut = ut; pp.W = Wp; pp.N = N; pp.C = C; pp.nbt = pl.nbt; pp.i_per_split = pl.i_per_split;
+            pp.X = w + pl.o_ds + pl.xs * r; pp.out = tmp;                       // dc = u_hat . ds^r
+            if ((rc = run_pass(pl, kModeL, pp, w, st))) return rc;
+            const long n = (long)pl.nbt * N * 32;
+            {
+                LaunchScope ls_(kcSoftmax, st);
+                // the register-resident variant (114 registers) loses to the three-pass one here: the second and
+                // third passes hit L1, and occupancy matters more than the re-reads (measured 1.9 vs 1.0 ms)
+                if (C <= 16) k_softmax_bwd_reg<16><<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+                else if (C <= 48 && g_tune_sbstaged) {
+                    const size_t smem = (size_t)4 * 2 * C * 32 * sizeof(float);
+                    CAPS_SET_SMEM(k_softmax_bwd_staged<48>, smem);
+                    const long nblocks = (long)pl.nbt * N;
+                    k_softmax_bwd_staged<48><<<cdiv(nblocks, 4), 128, smem, st>>>(c_r, tmp, beta_next, beta_r, C, nblocks);
+                } else k_softmax_bwd<<<cdiv(n, 128), 128, 0, st>>>(c_r, tmp, beta_next, beta_r, N, C, pl.nbt);
+            }
+            LAUNCH_CHECK();
+            pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
+            if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
         }
-        LAUNCH_CHECK();
-        pp.X = nullptr; pp.coef = beta_r; pp.out = part;                    // dv^{r-1} = sum_i beta u_hat
-        if ((rc = run_pass(pl, kModeA, pp, w, st))) return rc;
-        if ((rc = launch_dsquash(pl, part, nullptr, nullptr, 0.f, nullptr, nullptr, w + pl.o_s + pl.xs * (r - 1),
+        if ((rc = launch_dsquash(pl, part, ISb, nullptr, nullptr, 0.f, nullptr, nullptr, w + pl.o_s + pl.xs * (r - 1),
                                  w + pl.o_ds + pl.xs * (r - 1), r == 1 ? ds0_scale : 1.f, st)))
             return rc;
     }
@@ -546,8 +634,27 @@ bool host_step_layout(HostStepLayout& L, int B, int N, int C, int K, int D, int 
     L.total = o;
     return true;
 }
-cudaStream_t g_copy_stream = nullptr;
-cudaEvent_t g_copy_ev[kHostMaxMb + 1];
+// one internal copy stream per device, created on first use (mutex); the events of a call are its own
+cudaStream_t g_copy_stream[kMaxDevices];
+std::mutex g_copy_mu;
+int copy_stream_for_current_device(cudaStream_t* out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(CAPS_E_UNSUPPORTED, "device ordinal %d beyond %d", dev, kMaxDevices);
+    std::lock_guard<std::mutex> lk(g_copy_mu);
+    if (!g_copy_stream[dev]) CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream[dev], cudaStreamNonBlocking));
+    *out = g_copy_stream[dev];
+    return 0;
+}
+struct CallEvents {          // per call: two host threads (or two devices) never share an event
+    cudaEvent_t ev[kHostMaxMb + 1] = {};
+    int n = 0;
+    int create(int count) {
+        for (n = 0; n < count; ++n) CUDA_TRY(cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming));
+        return 0;
+    }
+    ~CallEvents() { for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]); }
+};
 }  // namespace
 
 size_t caps_route_step_host_scratch_bytes(int B, int N, int C, int K, int D, int R) {
@@ -576,25 +683,23 @@ int caps_route_step_host(const float* u_host, const int64_t* y_host, const float
     const size_t row_u = (size_t)N * K, row_v = (size_t)C * D;
     const float scale = 1.f / (float)B;
     cudaStream_t cs = st;
+    CallEvents evs;
+    int rc;
     if (L.nmb > 1) {
-        if (!g_copy_stream) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
-            for (auto& e : g_copy_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        }
-        cs = g_copy_stream;
+        if ((rc = copy_stream_for_current_device(&cs))) return rc;
+        if ((rc = evs.create(kHostMaxMb + 1))) return rc;
         // the copy stream may only overwrite u/y once everything already queued on `st` is done
-        CUDA_TRY(cudaEventRecord(g_copy_ev[kHostMaxMb], st));
-        CUDA_TRY(cudaStreamWaitEvent(cs, g_copy_ev[kHostMaxMb], 0));
+        CUDA_TRY(cudaEventRecord(evs.ev[kHostMaxMb], st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, evs.ev[kHostMaxMb], 0));
     }
     CUDA_TRY(cudaMemcpyAsync(y_d, y_host, (size_t)B * 8, cudaMemcpyHostToDevice, cs));
     for (int m = 0, b0 = 0; m < L.nmb; b0 += L.mb[m], ++m) {
         CUDA_TRY(cudaMemcpyAsync(u_d + b0 * row_u, u_host + b0 * row_u, L.mb[m] * row_u * 4, cudaMemcpyHostToDevice, cs));
-        if (L.nmb > 1) CUDA_TRY(cudaEventRecord(g_copy_ev[m], cs));
+        if (L.nmb > 1) CUDA_TRY(cudaEventRecord(evs.ev[m], cs));
     }
-    int rc;
     for (int m = 0, b0 = 0; m < L.nmb; b0 += L.mb[m], ++m) {
         const int Bm = L.mb[m];
-        if (L.nmb > 1) CUDA_TRY(cudaStreamWaitEvent(st, g_copy_ev[m], 0));
+        if (L.nmb > 1) CUDA_TRY(cudaStreamWaitEvent(st, evs.ev[m], 0));
         float* dW_m = m == 0 ? dW_dev : dwt;
         if ((rc = caps_route_forward(u_d + b0 * row_u, W_dev, v_d + b0 * row_v, nullptr, ws, wsb, Bm, N, C, K, D, R, 1, stream))) return rc;
         if ((rc = caps_margin_loss(v_d + b0 * row_v, y_d + b0, scale, loss_d + m, nullptr, reinterpret_cast<float*>(base + L.o_lscr), Bm, C, D, stream))) return rc;

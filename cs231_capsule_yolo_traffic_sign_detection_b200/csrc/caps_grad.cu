@@ -10,8 +10,7 @@ int launch_grad_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     constexpr bool XREG = (M * DP <= 96);
     const size_t smem = ((size_t)2 * IT * JW * K * DP + (size_t)JW * kGradDuBatch * K * 32) * sizeof(float);
     auto kern = k_grad<K, DP, JW, IT, M, XREG>;
-    { static size_t attr_set = 0;   /* per instantiation; the attribute is per device function, set once (or when it grows) */ \
-          if (smem > attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; } }
+    CAPS_SET_SMEM(kern, smem);          // per instantiation and per device
     dim3 grid(cdiv(pl.N, IT), pl.JG), block(32 * JW);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();

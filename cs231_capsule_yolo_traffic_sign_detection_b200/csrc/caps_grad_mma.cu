@@ -394,9 +394,7 @@ int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     const size_t smem = ((size_t)gm_fixed_floats(JW) + (size_t)gm_stages(M, JW) * gm_stage_floats(M, JW)) * sizeof(float) +
                         16 * gm_stages(M, JW) + 32;
     auto kern = pl.D == 16 ? k_grad_mma<M, JW, false> : k_grad_mma<M, JW, true>;
-    { static bool attr_set[2] = {false, false};
-      bool& done = attr_set[pl.D == 16 ? 0 : 1];
-      if (!done) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; } }
+    if (pl.D == 16) CAPS_SET_SMEM(kern, smem); else CAPS_SET_SMEM(kern, smem);      // one cache per instantiation (and per device)
     dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * cdiv(pl.DP, 16), JW)), block(32 * JW + 32);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();

@@ -12,8 +12,7 @@ int launch_pass_t(const Plan& pl, int mode, const PassParams& pp, cudaStream_t s
 #define CAPS_LAUNCH_MODE(MODE)                                                                           \
     {                                                                                                    \
         auto kern = k_pass<K, DP, SPT, JW, MODE>;                                                        \
-        { static size_t attr_set = 0;   /* per instantiation; the attribute is per device function, set once (or when it grows) */ \
-          if (smem > attr_set) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; } }    \
+        CAPS_SET_SMEM(kern, smem);      /* per instantiation and per device */                           \
         kern<<<grid, block, smem, st>>>(pp);                                                             \
     }
     if (mode == kModeAUniform) CAPS_LAUNCH_MODE(kModeAUniform)

@@ -39,6 +39,18 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def assert_close_elementwise(a, b, rtol=1e-4, atol_frac=1e-6, what=''):
+    """|a - b| <= rtol |b| + atol_frac * max|b| for EVERY element: unlike rel_err (a global max-norm), this does not let
+    a large entry hide the relative error of a small one; atol_frac * max|b| is the floor below which an fp32 sum of
+    that magnitude has no bits left."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    tol = rtol * np.abs(b) + atol_frac * max(np.abs(b).max(), 1e-300)
+    bad = np.abs(a - b) > tol
+    assert not bad.any(), '%s: %d of %d elements outside rtol=%g atol=%g*max; worst excess %.3g' % (
+        what, int(bad.sum()), bad.size, rtol, atol_frac, float((np.abs(a - b) / tol).max()))
+
+
 def dark_pattern(shape, mul, mod):
     """integer-valued fp32 test pattern used by tests/golden/make_golden.py::make_dark_regroup
     (exact through any permutation; inputs are regenerated from it, the fixture stores outputs only)"""

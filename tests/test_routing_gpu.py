@@ -8,12 +8,22 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_names, load_golden, rel_err
+from conftest import assert_close_elementwise, golden_names, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
 TOL_V = 1e-5
 TOL_G = 1e-4
+KNOB_DEFAULTS = {'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning_knobs():
+    """The knobs are process-global: a test that fails between set and reset must not leak its setting into the next."""
+    yield
+    from cs231_capsule_yolo_traffic_sign_detection_b200 import _cabi
+    for k, v in KNOB_DEFAULTS.items():
+        _cabi.set_tuning(k, v)
 
 
 @pytest.fixture(scope='module')
@@ -142,7 +152,7 @@ def test_bit_reproducible_and_tuning_invariant(capsb):
             assert np.array_equal(r['du'], first['du'])
             assert rel_err(r['dW'], base['dW']) < 1e-5
         capsb._cabi.set_tuning('spt', 0)
-        for isplit in (1, 3, 64):
+        for isplit in (1, 3, 32):
             capsb._cabi.set_tuning('isplit', isplit)
             r = cuda_step(capsb, u, W, y, R, want_c=False)
             assert rel_err(r['v'], base['v']) < 1e-5
@@ -183,6 +193,122 @@ def test_tensor_core_and_fma_engines_agree(capsb):
         capsb._cabi.set_tuning('gradjw', 0)
     assert np.array_equal(alt['dW'], res['tensor']['dW'])
     assert rel_err(alt['du'], res['tensor']['du']) < 5e-6
+
+
+@pytest.mark.parametrize('dims', [
+    (200, 160, 43, 8, 16, 3),     # 6 capsule groups (cluster of 6), ragged sample quad, last group 3 capsules wide
+    (129, 97, 10, 8, 16, 4),      # cluster of 2, N not a multiple of the split granule
+    (64, 64, 5, 8, 16, 2),        # one group: cluster of 1
+    (300, 72, 64, 8, 16, 3),      # cluster of 8 (the portable maximum)
+    (40, 256, 43, 8, 12, 5),      # D = 12 padded to 16, R = 5
+    (31, 40, 65, 8, 16, 3),       # 9 groups: beyond the cluster limit -> must take the unfused path by itself
+])
+def test_fused_sweep_matches_unfused_and_oracle(capsb, dims):
+    """The cluster-fused sweep (logits -> softmax -> weighted sum in one kernel, partial normalisers exchanged through
+    distributed shared memory) and the three-kernel path are two implementations of reference models.py:75-79 and of
+    its backward: both inside the oracle's tolerance, and within fp32 round-off of each other."""
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = dims
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=sum(dims) + 1)
+    ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R)
+    res = {}
+    for fused in (1, 0):
+        capsb._cabi.set_tuning('fused', fused)
+        res[fused] = cuda_step(capsb, u, W, y, R)
+        for k, tol in (('v', TOL_V), ('c', TOL_V), ('du', TOL_G), ('dW', TOL_G)):
+            assert rel_err(res[fused][k], ref[k]) < tol, (fused, k)
+        assert abs(res[fused]['loss'] - ref['loss']) < TOL_V * max(1.0, abs(ref['loss']))
+        assert_close_elementwise(res[fused]['dW'], ref['dW'], what='dW fused=%d' % fused)
+        assert_close_elementwise(res[fused]['du'], ref['du'], what='du fused=%d' % fused)
+    for k in ('v', 'c', 'du', 'dW'):
+        assert rel_err(res[1][k], res[0][k]) < 5e-6, k
+    # i-split of the fused sweep only regroups the sum over input capsules
+    capsb._cabi.set_tuning('fused', 1)
+    capsb._cabi.set_tuning('isplit', 2)
+    alt = cuda_step(capsb, u, W, y, R)
+    for k in ('v', 'du', 'dW'):
+        assert rel_err(alt[k], res[1][k]) < 5e-6, k
+
+
+@pytest.mark.parametrize('B', [512])
+def test_benchmark_shape_against_oracle(capsb, B):
+    """The configuration bench.py reports (BASELINE.json configs[1]: 1152 -> 43 x 16, 3 iterations) at a batch of
+    several 128-sample tiles, every output -- v, c, du AND dW -- against the fp64 C oracle, max-norm and per element."""
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    N, C, K, D, R = 1152, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=77)
+    ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R)
+    r = cuda_step(capsb, u, W, y, R)
+    assert rel_err(r['v'], ref['v']) < TOL_V
+    assert rel_err(r['c'], ref['c']) < TOL_V
+    assert abs(r['loss'] - ref['loss']) < TOL_V * max(1.0, abs(ref['loss']))
+    assert rel_err(r['du'], ref['du']) < TOL_G
+    assert rel_err(r['dW'], ref['dW']) < TOL_G
+    assert_close_elementwise(r['v'], ref['v'], rtol=1e-5, atol_frac=1e-6, what='v')
+    assert_close_elementwise(r['du'], ref['du'], what='du')
+    assert_close_elementwise(r['dW'], ref['dW'], what='dW')
+
+
+def test_benchmark_shape_host_step_against_oracle(capsb):
+    """The end-to-end call bench.py times (caps_route_step_host, three pipelined micro-batches from B >= 2048) at the
+    benchmark shape, against the fp64 C oracle: loss, v, du and the micro-batch-summed dW."""
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = 2048 + 128, 1152, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=78)
+    ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R, want_c=False)
+    dev = torch.device('cuda')
+    step = capsb.HostStep(B, N, C, K, D, R)
+    Wd = torch.from_numpy(W).to(dev)
+    dWd = torch.empty_like(Wd)
+    uh, yh = torch.from_numpy(u).pin_memory(), torch.from_numpy(y).pin_memory()
+    vh, duh = torch.empty(B, C, D).pin_memory(), torch.empty(B, N, K).pin_memory()
+    loss = float(step(uh, yh, Wd, dWd, v_host=vh, du_host=duh)[0])
+    assert abs(loss - ref['loss']) < TOL_V * max(1.0, abs(ref['loss']))
+    assert rel_err(vh.numpy(), ref['v']) < TOL_V
+    assert rel_err(duh.numpy(), ref['du']) < TOL_G
+    assert rel_err(dWd.cpu().numpy(), ref['dW']) < TOL_G
+    assert_close_elementwise(dWd.cpu().numpy(), ref['dW'], what='dW')
+    assert_close_elementwise(duh.numpy(), ref['du'], what='du')
+
+
+def test_backward_validates_forward_state(capsb):
+    """caps_route_backward on a workspace no forward filled, filled for other dims, or filled without with_grad
+    returns CAPS_E_STATE (-4) instead of reading garbage; and it replays the engines the forward used even if the
+    tuning knobs changed in between."""
+    from oracle import routing_np as onp
+    from cs231_capsule_yolo_traffic_sign_detection_b200 import _cabi
+    L = _cabi.lib()
+    dev = torch.device('cuda')
+    B, N, C, K, D, R = 40, 64, 43, 8, 16, 3
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=4)
+    ut, Wt, yt = torch.from_numpy(u).to(dev), torch.from_numpy(W).to(dev), torch.from_numpy(y).to(dev)
+    nbytes = L.caps_route_workspace_bytes(B, N, C, K, D, R, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    P = lambda t: t.data_ptr()
+    v, du, dW = torch.empty(B, C, D, device=dev), torch.empty(B, N, K, device=dev), torch.empty_like(Wt)
+
+    def bwd(ws, b=B):
+        return L.caps_route_backward(P(ut), P(Wt), None, P(yt), 1.0 / B, None, P(du), P(dW), P(ws), ws.numel(), b, N, C, K, D, R, st)
+    fresh = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+    assert bwd(fresh) == -4 and b'no caps_route_forward' in L.caps_last_error()
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    assert L.caps_route_forward(P(ut), P(Wt), P(v), None, P(ws), nbytes, B, N, C, K, D, R, 0, st) == 0
+    assert bwd(ws) == -4                                   # forward ran without with_grad
+    assert L.caps_route_forward(P(ut), P(Wt), P(v), None, P(ws), nbytes, B, N, C, K, D, R, 1, st) == 0
+    assert bwd(ws, b=B - 8) == -4                          # other dims
+    # knobs flipped between forward and backward: the backward must still use what the forward prepared
+    _cabi.set_tuning('tc', 0)
+    _cabi.set_tuning('fused', 0)
+    assert bwd(ws) == 0
+    torch.cuda.synchronize()
+    ref = cuda_step(capsb, u, W, y, R, want_c=False)       # knobs at defaults again?  no: still flipped -> FMA engines
+    _cabi.set_tuning('tc', 1)
+    _cabi.set_tuning('fused', 1)
+    assert rel_err(dW.cpu().numpy(), ref['dW']) < 5e-6
+    assert rel_err(du.cpu().numpy(), ref['du']) < 5e-6
 
 
 def test_batch_permutation_and_additivity_at_full_size(capsb):
