@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- capsule-routing samples/sec, fwd+bwd, on N B200s (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--workload cfg2|cfg1|cfg3|cfg3_head]
 
 A "step" is one pass of the hot path over one batch of synthetic input: routing forward
 (reference models.py:70-79), margin loss (loss_fns.py:12-17,23), backward to du and dW
@@ -13,8 +13,16 @@ Prints ONE JSON line (rank 0).  `value` times K steps with inputs resident in HB
 max over ranks); `e2e` times the same K steps through the host-buffer C-ABI call
 (caps_route_step_host: H2D of u,y from pinned memory and D2H of the loss inside the timed region);
 `roofline` is for the dominant kernel (the pass kernel) from CUDA events recorded around every
-launch in the timed region; `cpu_baseline` is the oracle's op-for-op torch port of the reference
-path on this box's host cores over a bounded sample.  `--impl reference` times only that CPU path.
+launch in the timed region; `cpu_baseline` / `--impl reference` time the UNMODIFIED reference layer (baseline/_ref, brought along by
+baseline/install_reference.py; `kind: "reference"`) on this box's host cores over a bounded sample -- or the
+oracle's op-for-op torch port (`kind: "port"`) when the reference is not installed.  `eager_b200` is the same
+unmodified reference run eagerly on the B200 (informational second baseline).  After the timed region a 64-sample
+slice of the benchmarked batch is checked against the fp64 C oracle (`parity_checked`).
+
+Other workloads (not the driver's line; numbers go to profiles/): `--workload cfg1` the reference's CapsNet train
+step at batch 16, `--workload cfg3` its DarkCapsuleNet step at batch 32 x 224^2 (both: reference model code with
+`models.CapsuleLayer` replaced by the B200-native layer, next to the unmodified reference on the CPU and eagerly on
+the GPU), `--workload cfg3_head` the DarkCapsuleNet head's routing shape alone.
 """
 import argparse
 import ctypes
@@ -106,28 +114,43 @@ class ClockSampler:
 # CPU reference arm / cpu_baseline (the ONLY places bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_fn(sample):
-    import numpy as np
+    """-> (step(), threads, kind): one fwd + margin loss + bwd of a `sample`-sized micro-batch on the host cores.
+    kind 'reference': the unmodified reference CapsuleLayer + capsule_loss from baseline/_ref;
+    kind 'port': oracle/routing_torch.py (same ATen ops, op for op) when the reference is not installed."""
     import torch
     from oracle import routing_np as onp
-    from oracle import routing_torch as ot
     torch.set_num_threads(os.cpu_count() or 1)
     u, W, y = onp.make_inputs(sample, N_NODES, N_CAPS, IN_C, OUT_C, seed=0)
-    ut, Wt, yt = torch.from_numpy(u), torch.from_numpy(W)[None], torch.from_numpy(y)
+    ut, yt = torch.from_numpy(u), torch.from_numpy(y)
+    try:
+        from baseline import refload, workloads
+        ref_ok = refload.load() is not None
+    except Exception:
+        ref_ok = False
+    if ref_ok:
+        ref_step = workloads.make_routing_reference_step(torch.device('cpu'), N_NODES, N_CAPS, IN_C, OUT_C, N_ITER)
+        Wt = torch.from_numpy(W)
+
+        def step():
+            return ref_step(ut, Wt, yt)
+        return step, torch.get_num_threads(), 'reference'
+    from oracle import routing_torch as ot
+    W5 = torch.from_numpy(W)[None]
 
     def step():
-        return ot.routing_step_t(ut, Wt, yt, N_ITER)
-    return step, torch.get_num_threads()
+        return ot.routing_step_t(ut, W5, yt, N_ITER)
+    return step, torch.get_num_threads(), 'port'
 
 
 def run_cpu_baseline(sample=64, reps=2):
     """Times the torch op-for-op port of the reference path (oracle/routing_torch.py) on the host."""
-    step, threads = cpu_reference_step_fn(sample)
+    step, threads, kind = cpu_reference_step_fn(sample)
     step()                                   # warm-up (allocator, thread pool)
     t0 = time.perf_counter()
     for _ in range(reps):
         step()
     dt = (time.perf_counter() - t0) / reps
-    return {'value': sample / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+    return {'value': sample / dt, 'unit': UNIT, 'cores': threads, 'kind': kind,
             'sample': '%d steps of a %d-sample micro-batch of the same workload (reference needs ~65 MB/sample; '
                       'its samples/s is flat in batch)' % (reps, sample),
             'ms_per_microbatch': dt * 1e3}
@@ -137,7 +160,7 @@ def main_reference(args, rank, world):
     if rank != 0:
         return 0
     sample = args.cpu_sample
-    step, threads = cpu_reference_step_fn(sample)
+    step, threads, kind = cpu_reference_step_fn(sample)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -150,9 +173,11 @@ def main_reference(args, rank, world):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args.batch),
-                   'note': 'reference CPU path (torch op-for-op port in oracle/routing_torch.py; the Python '
-                           'reference cannot travel to the GPU box); each step is a %d-sample micro-batch' % sample},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                   'note': ('reference CPU path: the UNMODIFIED reference CapsuleLayer + capsule_loss (baseline/_ref)'
+                            if kind == 'reference' else
+                            'reference CPU path: torch op-for-op port (oracle/routing_torch.py; baseline/_ref not installed)')
+                           + '; each step is a %d-sample micro-batch' % sample},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': kind,
                          'sample': '%d-sample micro-batch per step' % sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -268,6 +293,43 @@ def main_gpu(args, rank, world, device):
     if rank != 0:
         return 0
 
+    # ---- parity of THIS run: a 64-sample slice of the benchmarked batch against the fp64 C oracle ------------------
+    # (samples are independent: v and du of a sample do not depend on its batch-mates; 1/B is the loss scale)
+    parity = {'parity_checked': False}
+    try:
+        import numpy as np
+        from oracle import routing_c as oc
+        step_device()
+        torch.cuda.synchronize()
+        ns = min(64, B)
+        ref = oc.routing_step(u_host[:ns].numpy().astype(np.float64), W.cpu().numpy().astype(np.float64),
+                              y_host[:ns].numpy(), R, inv_batch=1.0 / B, want_c=False)
+
+        def rel(a, b):
+            return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+        ev, eu = rel(v[:ns].cpu().numpy(), ref['v']), rel(du[:ns].cpu().numpy(), ref['du'])
+        parity = {'parity_checked': bool(ev < 1e-5 and eu < 1e-4), 'parity': {'samples': ns, 'rel_err_v': ev, 'rel_err_du': eu,
+                  'tolerance': 'v 1e-5, du 1e-4 (max-norm relative, vs the fp64 C oracle); dW is covered by tests/ at B=512 and 2176'}}
+    except Exception as e:       # the checker must never take the measurement down
+        parity = {'parity_checked': False, 'parity': {'error': repr(e)[:200]}}
+
+    # ---- second, informational baseline: the UNMODIFIED reference layer run eagerly on this B200 -------------------
+    eager = None
+    if not args.no_eager:
+        try:
+            from baseline import workloads
+            mb = min(args.eager_batch, B)
+            ref_step = workloads.make_routing_reference_step(device, N, C, K, D, R)
+            ue, ye = u[:mb].contiguous(), y[:mb].contiguous()
+            sec = workloads.time_steps(lambda: ref_step(ue, W, ye), 3, 2, True)
+            eager = {'value': mb / sec, 'unit': UNIT, 'ms_per_microbatch': sec * 1e3, 'micro_batch': mb,
+                     'what': 'reference models.CapsuleLayer + loss_fns.capsule_loss, unmodified (baseline/_ref), eager PyTorch on the same GPU; '
+                             'its autograd state is ~65 MB per sample, hence the micro-batch'}
+            del ref_step, ue, ye
+            torch.cuda.empty_cache()
+        except Exception as e:
+            eager = {'unavailable': repr(e)[:200]}
+
     # ---- rooflines --------------------------------------------------------------------------
     peaks = {}
     try:
@@ -363,6 +425,103 @@ def main_gpu(args, rank, world, device):
         'roofline': roofline, 'roofline_fp32': roofline_fp32, 'roofline_softmax': roofline_softmax, 'roofline_step': roofline_step,
         'kernel_ms_per_step': per_class, 'profiled_ms_per_step': ms_prof / args.steps,
         'cpu_baseline': cpu,
+        'eager_b200': eager,
+    }
+    line.update(parity)
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# full-model workloads: BASELINE.json configs[0] (cfg1), configs[2] (cfg3) and configs[3] (cfg3 with --gpus N)
+# ------------------------------------------------------------------------------------------------
+def main_model(args, rank, world, device):
+    """The reference's own train step (main.py:55-77: H2D of the numpy batch, forward, loss, .cpu() of the prediction,
+    zero_grad / backward / Adam step, loss.item()) on the reference's own model code, with `models.CapsuleLayer`
+    replaced by the B200-native layer; next to it the unmodified reference eagerly on the same GPU and on the host
+    cores.  With --gpus N (cfg3 = BASELINE.json configs[3]) every rank steps on its own shard and ALL gradients
+    (backbone + routing weights) are averaged through one flat NCCL bucket per step."""
+    import torch
+    import torch.distributed as dist
+    from baseline import refload, workloads
+    if refload.load() is None:
+        if rank == 0:
+            print(json.dumps({'workload': args.workload, 'unavailable': 'reference not installed under baseline/_ref (run __graft_entry__.build() where /root/reference is mounted)'}))
+        return 0
+    cfg = args.workload
+    B = args.batch if args.batch != 8192 else (16 if cfg == 'cfg1' else 32)
+    torch.backends.cudnn.allow_tf32 = False            # fp32 convolutions on every arm, like the CPU reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x, y = (workloads.synth_cfg1 if cfg == 'cfg1' else workloads.synth_cfg3)(B, seed=rank)
+
+    def build(dev, dropin, **kw):
+        if cfg == 'cfg1':
+            return workloads.make_cfg1_step(dev, dropin=dropin)[0]
+        return workloads.make_cfg3_step(dev, dropin=dropin, **kw)[0]
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step(x, y)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = step(x, y)
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / steps
+        if world > 1:
+            t = torch.tensor([sec], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t)
+        return sec, loss
+
+    out = {}
+    variants = [('dropin', dict(dropin=True))]
+    if cfg == 'cfg3':
+        variants.append(('dropin_fused_tail', dict(dropin=True, fused_tail=True)))
+    if world == 1:
+        variants.append(('reference_eager_b200', dict(dropin=False)))
+    for name, kw in variants:
+        if cfg == 'cfg3':
+            kw = dict(kw, world=world)
+        step = build(device, **kw)
+        sec, loss = timed(step, args.steps, args.warmup)
+        out[name] = {'samples_per_s': world * B / sec, 'ms_per_step': sec * 1e3, 'loss': loss}
+        del step
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return 0
+    cpu = None
+    if not args.no_cpu and world == 1:
+        threads = workloads.cpu_threads()
+        Bc = B if cfg == 'cfg1' else min(B, 4)           # a DarkCapsuleNet step is ~90 GFLOP per sample: bounded sample
+        xc, yc = x[:Bc], y[:Bc]
+        step = build(torch.device('cpu'), False)
+        step(xc, yc)
+        t0 = time.perf_counter()
+        n = 2
+        for _ in range(n):
+            step(xc, yc)
+        sec = (time.perf_counter() - t0) / n
+        cpu = {'value': Bc / sec, 'unit': 'samples/s', 'cores': threads, 'kind': 'reference',
+               'sample': '%d steps of batch %d of the same workload' % (n, Bc), 'ms_per_step': sec * 1e3}
+    main_v = out['dropin']
+    line = {
+        'metric': 'train-step samples/sec (reference main.py:55-77 step on the reference model, B200-native CapsuleLayer dropped in)',
+        'value': main_v['samples_per_s'], 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': main_v['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': ('configs[0]: CapsNet (conv1 -> primary caps -> routing 1296->43x16 -> decoder), recon on, Adam, batch %d' % B)
+                   if cfg == 'cfg1' else
+                   ('configs[%d]: DarkCapsuleNet (5-conv backbone -> regroup -> routing 512->1x5 per cell) at 224x224, --recon --no_metric, Adam, batch %d per GPU'
+                    % (3 if world > 1 else 2, B)),
+                   'parallelism': 'dp%d' % world,
+                   'allreduce': 'one flat NCCL bucket per step over backbone + routing gradients (parallel.GradBucket)' if world > 1 else None},
+        'e2e': {'value': main_v['samples_per_s'], 'unit': 'samples/s', 'h2d_bytes_per_step': int(x.nbytes + y.nbytes),
+                'd2h_bytes_per_step': int(4 + (B * 43 * 4 if cfg == 'cfg1' else B * 49 * 5 * 4)),
+                'note': 'the step IS end to end: numpy batch -> device, prediction and loss -> host, every step'},
+        'variants': out, 'cpu_baseline': cpu,
     }
     print(json.dumps(line))
     return 0
@@ -377,6 +536,11 @@ def main():
     ap.add_argument('--batch', type=int, default=8192, help='per-GPU batch (weak scaling)')
     ap.add_argument('--cpu-sample', type=int, default=64, help='micro-batch of the CPU baseline')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-eager', action='store_true', help='skip the eager-reference-on-GPU leg')
+    ap.add_argument('--eager-batch', type=int, default=256, help='micro-batch of the eager reference on the GPU')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg1', 'cfg3', 'cfg3_head'],
+                    help='cfg2 (default, the line the driver reads): routing layer alone; cfg1: CapsNet train step B=16; '
+                         'cfg3: DarkCapsuleNet train step B=32 @224; cfg3_head: the DarkCapsuleNet head routing shape alone')
     ap.add_argument('--spt', type=int, default=0)
     ap.add_argument('--isplit', type=int, default=0)
     ap.add_argument('--tune', default='', help='comma list name=value passed to caps_set_tuning')
@@ -392,7 +556,15 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     rank, world, device = init_from_env()
+    if args.workload == 'cfg3_head':
+        # the DarkCapsuleNet head (reference models.py:368-370, :398): routing batch 32 * 49 cells, 512 -> 1 x 5
+        global N_NODES, N_CAPS, OUT_C
+        N_NODES, N_CAPS, OUT_C = 512, 1, 5
+        if args.batch == 8192:
+            args.batch = 1568
     try:
+        if args.workload in ('cfg1', 'cfg3'):
+            return main_model(args, rank, world, device)
         return main_gpu(args, rank, world, device)
     finally:
         import torch.distributed as dist

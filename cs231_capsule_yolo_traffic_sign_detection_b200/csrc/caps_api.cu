@@ -152,7 +152,8 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.i_per_split = cdiv(cdiv(N, is), kPassIC) * kPassIC;
     p.IS = cdiv(N, p.i_per_split);
     p.xs = round64((size_t)p.nbt * C * p.DP * 32);
-    p.cs = round64((size_t)p.nbt * N * C * 32);
+    p.CSmax = fused_shape_ok(C, p.DP, p.tc_ok) ? cdiv(C, 8) * 8 : C;       // the fused sweep pads coefficient rows to whole capsule groups
+    p.cs = round64((size_t)p.nbt * N * p.CSmax * 32);
     p.us = round64((size_t)p.nbt * N * K * 32);
     // ---- layout: depends on (dims, with_grad) only -------------------------------------------------------------
     const int part_slots = std::min(kMaxSplits, max_is);
@@ -270,6 +271,12 @@ int caps_set_tuning(const char* name, int value) {
         return 0;
     }
     if (!strcmp(name, "tcdbg")) { g_tc_dbg = value; return 0; }
+    if (!strcmp(name, "fsdbg")) { g_fs_dbg = value; return 0; }
+    if (!strcmp(name, "fsinfo")) {          // prints what the fused sweep would do for C = value (diagnostics)
+        fprintf(stderr, "[caps] fused sweep: cluster of %d CTAs, capacity fwd %d / bwd %d clusters\n", cdiv(value, 8),
+                fused_cluster_capacity(cdiv(value, 8), false), fused_cluster_capacity(cdiv(value, 8), true));
+        return 0;
+    }
     if (!strcmp(name, "tcstages")) { if (value < 2 || value > 12) return fail(CAPS_E_BADARG, "tcstages must be in [2,12]"); g_tc_stages = value; return 0; }
     if (!strcmp(name, "gradmma")) { g_tune_gradmma = value != 0; return 0; }
     if (!strcmp(name, "gradjw")) {
@@ -359,7 +366,7 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
             if ((rc = launch_squash(pl, part, ISf, 1.f, s_r, v_r, vsum, 1, last ? v : nullptr, st))) return rc;
             if (last && c_out != nullptr) {
                 LaunchScope ls_(kcOther, st);
-                if ((rc = launch_coef_public(pl, c_r, c_out, st))) return rc;
+                if ((rc = launch_coef_public(pl, c_r, pl.CSmax, c_out, st))) return rc;
             }
             continue;
         }
@@ -473,6 +480,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     GradParams gp{};
     gp.ut = ut; gp.W = Wp; gp.dW = dW; gp.du_part = w + pl.o_dupart;
     gp.N = N; gp.C = C; gp.D = D; gp.DP = pl.DP; gp.nbt = pl.nbt;
+    gp.CS = pl.fused ? pl.CSmax : C;
     int m = 0;
     for (int r = 0; r < Re; ++r) {                                          // c^r (x) ds^r
         gp.coef[m] = (r == 0) ? nullptr : w + pl.o_c + pl.cs * (r - 1);

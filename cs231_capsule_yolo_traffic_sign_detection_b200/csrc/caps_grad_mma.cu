@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
                     for (int m = 0; m < M; ++m)
                         if (p.coef[m] != nullptr) {
                             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                         ::"r"(cd), "l"(p.coef[m] + (ti * p.C + jfirst) * kLanes), "r"(cbytes), "r"(bar) : "memory");
+                                         ::"r"(cd), "l"(p.coef[m] + (ti * p.CS + jfirst) * kLanes), "r"(cbytes), "r"(bar) : "memory");
                             cd += JW * 128;
                         }
                 }

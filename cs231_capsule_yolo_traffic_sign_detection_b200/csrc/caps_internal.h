@@ -45,6 +45,7 @@ constexpr int kMaxSplits = 32;     // splits of the i range any sweep may use (s
 // backward (caps_api.cu: forward records).
 struct Plan {
     int B, N, C, K, D, R, Reff, DP, JW, JG, SPT, nbt, ntg, IS, i_per_split, M;
+    int CSmax;                         // capsules per coefficient row the layout reserves (C, or C rounded up to 8 where the fused sweep may run)
     bool pad_w, with_grad, use_tc, tc_ok, fused;
     size_t xs, cs, us;                 // floats per X / coef / ut array
     // offsets (floats) into the workspace
@@ -67,10 +68,13 @@ int launch_prep_u_tc(const Plan& pl, const float* u, float* ua, float* ut, cudaS
 int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st);
 int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st);
 // caps_sweep_fused.cu: one cluster-fused sweep per routing iteration (logits -> softmax -> weighted sum)
+extern int g_fs_dbg;                    // timing experiments only
 bool fused_supported(const Plan& pl);
+bool fused_shape_ok(int C, int DP, bool tc_ok);       // depends on the dims only (sizes the coefficient rows)
+int fused_cluster_capacity(int jg, bool bwd);
 int fused_pick_splits(const Plan& pl, bool bwd, int forced);
 int launch_sweep_fused(const Plan& pl, bool bwd, const float* ua, const float* wb, const float* X, const float* coef_in,
                        const float* beta_in, float* coef_out, float* part, int IS, cudaStream_t st);
-int launch_coef_public(const Plan& pl, const float* coef, float* c_pub, cudaStream_t st);
+int launch_coef_public(const Plan& pl, const float* coef, int CS, float* c_pub, cudaStream_t st);
 
 }  // namespace caps

@@ -573,6 +573,7 @@ struct GradParams {
     float cconst[kGradMaxM];
     int N, C, D, nbt;
     int DP;                            // padded D: row length of W and of the X arrays (k_grad_mma)
+    int CS;                            // capsules per coefficient row (C, or C rounded up to 8 when the fused sweep wrote the arrays)
 };
 
 // transpose-reduce: every lane holds 32 values; lane l returns sum over lanes of vals[l].
@@ -653,7 +654,7 @@ __global__ void __launch_bounds__(32 * JW, 1) k_grad(GradParams p) {
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
                         const float al = p.coef[m] != nullptr
-                                             ? __ldg(p.coef[m] + (((size_t)tile * p.N + i) * p.C + j) * kLanes + lane)
+                                             ? __ldg(p.coef[m] + (((size_t)tile * p.N + i) * p.CS + j) * kLanes + lane)
                                              : p.cconst[m];
                         if (XREG) {
 #pragma unroll

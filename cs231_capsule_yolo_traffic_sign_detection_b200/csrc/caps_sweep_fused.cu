@@ -12,18 +12,19 @@
 //     P1(n)   u_hat = tcgen05.ld of the stage's accumulator (3xTF32 MMA, as in caps_pass_tc.cu)
 //             FWD: e_j = exp(u_hat_j . V_j)             z = sum of the warp's 4 e_j
 //             BWD: dc_j = u_hat_j . ds_j               z = sum of c_j dc_j        (c: saved by the forward)
-//             z -> shared; the exchange warp adds the two column halves and sends the 128-sample row (512 B)
-//             to every CTA of the cluster with cp.async.bulk (shared::cta -> shared::cluster), which completes
-//             a transaction barrier at the receiver.
+//             z -> shared; the exchange warp adds the two column halves and stores the 128-sample row (512 B)
+//             into every CTA of the cluster with st.async (registers -> shared::cluster), which credits a
+//             transaction barrier at the receiver as the bytes land.
 //     P2(n-2) Z = sum over the cluster's rows (fixed order: every CTA gets bit-identical Z)
 //             FWD: c_j = e_j / Z          -> stored once for the backward     acc_j += c_j u_hat_j
 //             BWD: beta_j = beta'_j + c_j (dc_j - Z) -> stored once           acc_j += beta_j u_hat_j
 //             (u_hat is read again from TMEM: the accumulator ring is 4 deep, the exchange takes < 2 stages)
 //
 // So per iteration the [B,N,C] data is written ONCE (what the backward needs) and never re-read by the forward.
-// Flow control of the exchange ring needs no credits: a CTA can only send the row of stage n+4 after every CTA
-// of the cluster has consumed the row of stage n (its P1(n+4) follows its own P2(n+2), which needed every peer's
-// row n+2, which each peer sent after its own P2(n)); see DESIGN.md section 3.4.
+// Flow control of the exchange ring needs no credits: an iteration runs P1(it) and then P2(it-2), so a CTA sends
+// the row of stage m only after its own P2(m-3), which needed every peer's row m-3, which each peer sent after its
+// own P2(m-6): when row m arrives, rows <= m-6 have been consumed everywhere, and the ring holds 8 >= 6 rows
+// (DESIGN.md section 3.4).
 //
 // softmax is evaluated without the max subtraction (exp2 of the logit times log2 e, clamped at 2^120): the logits
 // are u_hat . (v^0 + .. + v^{r-1}) with |v| < 1, so they stay far inside the fp32 exponent range for any weights
@@ -41,28 +42,29 @@ constexpr int kFsEpiWarps = 8;
 constexpr int kFsThreads = 384;            // warps 0-7 epilogue, 8 producer, 9 MMA issuer, 10 exchange, 11 idle
 constexpr int kFsAccum = 4;                // TMEM ring: 4 accumulators x 128 columns
 constexpr int kFsSkew = 2;                 // stages between P1 and P2 of the same input capsule
-constexpr int kFsZSlots = 4;               // exchange ring depth (>= 2 * kFsSkew: the credit-free argument above)
+constexpr int kFsZSlots = 8;               // exchange ring depth (>= 3 * kFsSkew: the credit-free argument in DESIGN.md 3.4)
 constexpr int kFsMaxCluster = 8;           // portable cluster size: C <= 64 at 8 capsules per CTA
 constexpr int kFsMaxStages = 12;
 constexpr int kFsOperandBytes = 16384;     // A (8 KB: u hi/lo) + B (8 KB: W hi/lo), layouts of caps_pass_tc.cu
 constexpr int kFsCoefBytes = 4096;         // [4 lane tiles][8 capsules][32 lanes] floats
 __host__ __device__ constexpr int fs_stage_bytes(bool bwd) { return kFsOperandBytes + (bwd ? 2 * kFsCoefBytes : 0); }
-constexpr int kFsZpartBytes = kFsZSlots * 2 * 128 * 4;
-constexpr int kFsZcombBytes = kFsZSlots * 128 * 4;
-constexpr int kFsZrecvBytes = kFsZSlots * kFsMaxCluster * 128 * 4;
-constexpr int kFsEringBytes = (kFsSkew + 1) * kFsEpiWarps * 4 * 32 * 4;
-constexpr int kFsBarBytes = 8 * (2 * kFsMaxStages + 2 * kFsAccum + 2 * kFsZSlots) + 16;
-constexpr int kFsFixedBytes = kFsZpartBytes + kFsZcombBytes + kFsZrecvBytes + kFsEringBytes + kFsBarBytes;
+constexpr int kFsZpartBytes = kFsZSlots * 2 * 128 * 4;                    // [slot][column half][128 samples]
+constexpr int kFsZrecvBytes = kFsZSlots * kFsMaxCluster * 128 * 4;        // [slot][sender rank][128 samples]
+constexpr int kFsEringBytes = (kFsSkew + 1) * kFsEpiWarps * 4 * 32 * 4;   // [skew+1][warp][4][32]
+constexpr int kFsBarBytes = 8 * (2 * kFsMaxStages + 2 * kFsAccum + 2 * kFsZSlots) + 16;     // + tcgen05.alloc slot + base slot
+constexpr int kFsFixedBytes = kFsZpartBytes + kFsZrecvBytes + kFsEringBytes + kFsBarBytes;
 
 struct FusedParams {
     const float* ua;        // [ntq][N][2][2][128][4]
     const float* wb;        // [N][JG][2][2][128][4]
     const float* X;         // FWD: sum of v so far; BWD: ds^r     [nbt][C][4][32][4]
-    const float* coef_in;   // BWD: c^r                            [nbt][N][C][32]
+    const float* coef_in;   // BWD: c^r                            [nbt][N][8 JG][32]  (rows padded to whole capsule groups;
+                            //                                      the padding capsules hold exact zeros)
     const float* beta_in;   // BWD: beta^{r+1} or nullptr
     float* coef_out;        // FWD: c^r (nullptr: not wanted); BWD: beta^r
     float* part;            // [IS][nbt][C][4][32][4]
     int N, C, JG, nbt, i_per_split, ns;
+    int dbg;                // TIMING EXPERIMENTS ONLY (tuning knob "fsdbg"): 1 = no exchange at all (Z = 1), 2 = no coefficient stores
 };
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
@@ -84,27 +86,42 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 16 bytes from this thread's registers into another CTA's shared memory; the receiver's transaction barrier is
+// credited with the 16 bytes when they have landed (no shared-memory staging, no proxy fence on the sender's side)
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, float4 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                   "r"(__float_as_uint(v.w)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// Shared-memory map (byte offsets from the dynamic base; the fixed part first so that every address the epilogue
+// touches is `one base register + compile-time constant + small ring offset`):
+constexpr uint32_t kOffZpart = 0;                                   // [slot 8][column half 2][128 samples] floats
+constexpr uint32_t kOffZrecv = kOffZpart + kFsZpartBytes;           // [slot 8][sender rank 8][128] floats; ranks >= JG stay zero
+constexpr uint32_t kOffEring = kOffZrecv + kFsZrecvBytes;           // [eslot 3][column half 2][capsule 4][128] floats: P1 -> P2
+constexpr uint32_t kOffBars = kOffEring + kFsEringBytes;
+constexpr uint32_t kOffSmemFull = kOffBars;                         // [kFsMaxStages]
+constexpr uint32_t kOffSmemEmpty = kOffSmemFull + 8 * kFsMaxStages; // [kFsMaxStages]
+constexpr uint32_t kOffTmemFull = kOffSmemEmpty + 8 * kFsMaxStages; // [kFsAccum]
+constexpr uint32_t kOffTmemEmpty = kOffTmemFull + 8 * kFsAccum;     // [kFsAccum]
+constexpr uint32_t kOffZlocal = kOffTmemEmpty + 8 * kFsAccum;       // [kFsZSlots]: the 8 epilogue warps wrote their partials
+constexpr uint32_t kOffZfull = kOffZlocal + 8 * kFsZSlots;          // [kFsZSlots]: every CTA's row has landed (transaction count)
+constexpr uint32_t kOffTmemSlot = kOffZfull + 8 * kFsZSlots;        // tcgen05.alloc result
+constexpr uint32_t kOffBaseSlot = kOffTmemSlot + 4;                 // the base address itself, read back (see below)
+constexpr uint32_t kOffStages = (kFsFixedBytes + 1023) & ~1023u;    // [ns][A 8 KB | B 8 KB | (BWD) c 4 KB | beta' 4 KB]
+static_assert(kOffBaseSlot + 4 <= kOffStages, "fixed region overflows");
 
 template <bool BWD>
 __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int kStageBytes = fs_stage_bytes(BWD);
+    constexpr uint32_t kStageBytes = fs_stage_bytes(BWD);
     const int ns = p.ns;
-    const uint32_t stages = smem_u32(smem_raw);
-    const uint32_t zpart = stages + (uint32_t)ns * kStageBytes;      // [slot][column half][128 samples]
-    const uint32_t zcomb = zpart + kFsZpartBytes;                    // [slot][128]: the row this CTA sends
-    const uint32_t zrecv = zcomb + kFsZcombBytes;                    // [slot][sender rank][128]
-    const uint32_t ering = zrecv + kFsZrecvBytes;                    // [skew+1][warp][4][32]: e_j (FWD) / dc_j (BWD) from P1 to P2
-    const uint32_t bars = ering + kFsEringBytes;
-    const uint32_t smem_full = bars;                                 // [kFsMaxStages]
-    const uint32_t smem_empty = smem_full + 8 * kFsMaxStages;        // [kFsMaxStages]
-    const uint32_t tmem_full = smem_empty + 8 * kFsMaxStages;        // [kFsAccum]
-    const uint32_t tmem_empty = tmem_full + 8 * kFsAccum;            // [kFsAccum]
-    const uint32_t zlocal = tmem_empty + 8 * kFsAccum;               // [kFsZSlots]: the 8 epilogue warps wrote their partials
-    const uint32_t zfull = zlocal + 8 * kFsZSlots;                   // [kFsZSlots]: every CTA's row has landed (transaction count)
-    const uint32_t tmem_slot = zfull + 8 * kFsZSlots;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - stages));
-
+    const uint32_t base0 = smem_u32(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int jg = blockIdx.x, tq = blockIdx.z;                      // cluster = the JG CTAs along x: rank == jg
     const int i_begin = blockIdx.y * p.i_per_split;
@@ -112,43 +129,51 @@ __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
     const int n_i = max(i_end - i_begin, 0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ns; ++s) { mbar_init(smem_full + 8 * s, 1); mbar_init(smem_empty + 8 * s, BWD ? kFsEpiWarps + 1 : 1); }
-        for (int t = 0; t < kFsAccum; ++t) { mbar_init(tmem_full + 8 * t, 1); mbar_init(tmem_empty + 8 * t, kFsEpiWarps); }
-        for (int z = 0; z < kFsZSlots; ++z) { mbar_init(zlocal + 8 * z, kFsEpiWarps); mbar_init(zfull + 8 * z, 1); }
+        for (int s = 0; s < ns; ++s) { mbar_init(base0 + kOffSmemFull + 8 * s, 1); mbar_init(base0 + kOffSmemEmpty + 8 * s, BWD ? kFsEpiWarps + 1 : 1); }
+        for (int t = 0; t < kFsAccum; ++t) { mbar_init(base0 + kOffTmemFull + 8 * t, 1); mbar_init(base0 + kOffTmemEmpty + 8 * t, kFsEpiWarps); }
+        for (int z = 0; z < kFsZSlots; ++z) { mbar_init(base0 + kOffZlocal + 8 * z, kFsEpiWarps); mbar_init(base0 + kOffZfull + 8 * z, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base0 + kOffBaseSlot), "r"(base0) : "memory");
     }
+    for (int e = threadIdx.x; e < kFsZrecvBytes / 4; e += kFsThreads) sts_f32(base0 + kOffZrecv + 4 * e, 0.f);   // absent ranks add 0
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base0 + kOffTmemSlot), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_slot;
-    cluster_sync_all();                      // every CTA's barriers are initialised before any remote traffic
+    // The shared window address of this CTA is (0x400 | cluster rank << 24): cheap to rebuild on the uniform datapath, so
+    // ptxas rematerialises it (S2UR + ULEA, a dependent chain) at every use inside the register-starved epilogue loop.
+    // Reading it back through shared memory makes it an ordinary value that lives in one register.
+    uint32_t base, tmem_base;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(base) : "r"(base0 + kOffBaseSlot) : "memory");
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(base0 + kOffTmemSlot) : "memory");
+    cluster_sync_all();                      // every CTA's barriers and zeroed rows are in place before any remote traffic
 
     if (warp >= kFsEpiWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const uint32_t stages = base + kOffStages;
         if (warp == 8) {
             // ===== producer: one elected lane arms smem_full[s] and issues the stage's bulk copies =====
             const float* asrc = p.ua + ((size_t)tq * p.N + i_begin) * 2048;
             const float* bsrc = p.wb + ((size_t)i_begin * p.JG + jg) * 2048;
             const size_t bstep = (size_t)p.JG * 2048;
-            const int nj = min(8, p.C - jg * 8);
-            const uint32_t cbytes = (uint32_t)nj * 128u;
-            const size_t ctile = (size_t)p.N * p.C * kLanes;                  // coefficient floats per lane tile
-            const size_t coff = ((size_t)(tq * 4) * p.N + i_begin) * p.C * kLanes + (size_t)jg * 8 * kLanes;
+            const size_t CS = (size_t)p.JG * 8;                               // capsules per coefficient row (padded)
+            const uint32_t cbytes = 8u * 128u;                                // the CTA's 8 capsules x 32 lanes
+            const size_t ctile = (size_t)p.N * CS * kLanes;                   // coefficient floats per lane tile
+            const size_t coff = ((size_t)(tq * 4) * p.N + i_begin) * CS * kLanes + (size_t)jg * 8 * kLanes;
             const float* csrc = BWD ? p.coef_in + coff : nullptr;
             const float* esrc = (BWD && p.beta_in != nullptr) ? p.beta_in + coff : nullptr;
-            const size_t cstep = (size_t)p.C * kLanes;
+            const size_t cstep = CS * kLanes;
             const int nvt = min(4, p.nbt - tq * 4);                          // valid lane tiles of this quad (>= 1)
             const uint32_t txbytes = (uint32_t)kFsOperandBytes + (BWD ? (uint32_t)nvt * cbytes * (esrc ? 2u : 1u) : 0u);
             int s = 0;
             uint32_t ph = 1;
             for (int n = 0; n < n_i; ++n) {
-                mbar_wait_i(smem_empty + 8 * s, ph);
+                mbar_wait_i(base + kOffSmemEmpty + 8 * s, ph);
                 if (elect_one()) {
-                    const uint32_t dst = stages + (uint32_t)s * kStageBytes, bar = smem_full + 8 * s;
+                    const uint32_t dst = stages + (uint32_t)s * kStageBytes, bar = base + kOffSmemFull + 8 * s;
                     mbar_expect_tx(bar, txbytes);
                     bulk_g2s(dst, asrc, 8192, bar);
                     bulk_g2s(dst + 8192, bsrc, 8192, bar);
@@ -173,36 +198,36 @@ __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
             uint32_t sph = 0;
             for (int n = 0; n < n_i; ++n) {
                 const int t = n & (kFsAccum - 1);
-                mbar_wait_i(tmem_empty + 8 * t, ((n >> 2) & 1) ^ 1);
-                mbar_wait_i(smem_full + 8 * s, sph);
+                mbar_wait_i(base + kOffTmemEmpty + 8 * t, ((n >> 2) & 1) ^ 1);
+                mbar_wait_i(base + kOffSmemFull + 8 * s, sph);
                 tc_fence_after();
                 const uint64_t a_hi = desc0 + (uint64_t)((s * kStageBytes) >> 4);
                 const uint64_t a_lo = a_hi + (4096 >> 4), b_hi = a_hi + (8192 >> 4), b_lo = b_hi + (4096 >> 4);
-                umma_stage(tmem_base + (uint32_t)(t * 128), a_hi, a_lo, b_hi, b_lo, idesc, smem_empty + 8 * s, tmem_full + 8 * t);
+                umma_stage(tmem_base + (uint32_t)(t * 128), a_hi, a_lo, b_hi, b_lo, idesc, base + kOffSmemEmpty + 8 * s, base + kOffTmemFull + 8 * t);
                 if (++s == ns) { s = 0; sph ^= 1; }
             }
-        } else if (warp == 10) {
-            // ===== exchange: add the two column halves of a stage's partial normaliser, send the row to the cluster =====
+        } else if (warp == 10 && !(p.dbg & 1)) {
+            // ===== exchange: lane l adds the two column halves of samples 4l..4l+3 and stores the 16 bytes straight into
+            // every CTA's receive row (st.async: the data and the receiver's transaction count travel together) =====
             const uint32_t nrank = (uint32_t)p.JG;
-            for (int n = 0; n < n_i; ++n) {
-                const uint32_t slot = (uint32_t)n & (kFsZSlots - 1), par = ((uint32_t)n >> 2) & 1;
-                mbar_wait_i(zlocal + 8 * slot, par);
-                const uint32_t src = zpart + slot * 1024, dst = zcomb + slot * 512;
+            const uint32_t my_row = base + kOffZrecv + (uint32_t)jg * 512 + (uint32_t)lane * 16;       // + slot * 4096, in the receiver
+            uint32_t raddr[kFsMaxCluster], rbar[kFsMaxCluster];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t o = (uint32_t)(lane + 32 * k) * 4;
-                    sts_f32(dst + o, lds_f32(src + o) + lds_f32(src + 512 + o));
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the bulk copy's reads
-                __syncwarp();
-                if (elect_one()) {
-                    mbar_expect_tx(zfull + 8 * slot, nrank * 512u);
-                    const uint32_t rdst = zrecv + (slot * kFsMaxCluster + (uint32_t)jg) * 512, rbar = zfull + 8 * slot;
-                    for (uint32_t r = 0; r < nrank; ++r)
-                        asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(mapa_u32(rdst, r)), "r"(dst), "r"(512u), "r"(mapa_u32(rbar, r)) : "memory");
-                }
-                __syncwarp();
+            for (int r = 0; r < kFsMaxCluster; ++r) {
+                const uint32_t rr = (uint32_t)r < nrank ? (uint32_t)r : 0u;
+                raddr[r] = mapa_u32(my_row, rr);
+                rbar[r] = mapa_u32(base + kOffZfull, rr);
+            }
+            for (int n = 0; n < n_i; ++n) {
+                const uint32_t slot = (uint32_t)n & (kFsZSlots - 1), par = ((uint32_t)n >> 3) & 1;
+                mbar_wait_i(base + kOffZlocal + 8 * slot, par);
+                const float4 a = lds_v4(base + kOffZpart + slot * 1024 + (uint32_t)lane * 16);
+                const float4 b = lds_v4(base + kOffZpart + slot * 1024 + 512 + (uint32_t)lane * 16);
+                const float4 z = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+                if (lane == 0) mbar_expect_tx(base + kOffZfull + 8 * slot, nrank * 512u);
+#pragma unroll
+                for (int r = 0; r < kFsMaxCluster; ++r)
+                    if ((uint32_t)r < nrank) st_async_v4(raddr[r] + slot * 4096, z, rbar[r] + 8 * slot);
             }
         }
     } else {
@@ -212,6 +237,18 @@ __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
         const int tile = tq * 4 + q;
         const bool tvalid = tile < p.nbt;
         const int j0 = jg * 8 + jh * 4;
+        // No per-capsule predicates inside the loop: coefficient rows are padded to whole groups of 8 capsules, a capsule
+        // beyond C has W = 0 (u_hat = 0), X = 0, and (FWD) its exponent is clamped to -200 instead of +120 so that its
+        // e_j, its coupling and everything stored for it are exact zeros; (BWD) it then reads c = beta' = 0 back.
+        float lim[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            lim[jj] = (j0 + jj < p.C) ? 120.f : -200.f;
+            asm volatile("mov.b32 %0, %0;" : "+f"(lim[jj]));       // pin: ptxas would rebuild it from ctaid / tid every iteration
+        }
+        const bool has_beta = BWD && p.beta_in != nullptr;
+        const bool no_xchg = (p.dbg & 1) != 0;
+        const bool do_store = tvalid && p.coef_out != nullptr && !(p.dbg & 2);             // warp-uniform
         float X[4][16];                 // FWD: log2(e) * sum of v; BWD: ds
         float acc[4][16];
 #pragma unroll
@@ -230,89 +267,114 @@ __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
                     }
                 }
         }
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * 64);
-        const uint32_t my_zpart = zpart + (uint32_t)(jh * 128 + q * 32 + lane) * 4;       // + slot * 1024
-        const uint32_t my_zrecv = zrecv + (uint32_t)(q * 32 + lane) * 4;                   // + (slot * 8 + rank) * 512
-        const uint32_t my_ering = ering + (uint32_t)((warp * 4) * 32 + lane) * 4;          // + eslot * 4096 + jj * 128
-        const uint32_t my_coef = (uint32_t)kFsOperandBytes + (uint32_t)((q * 8 + jh * 4) * kLanes + lane) * 4;   // in a stage, + jj * 128
-        int s1 = 0, s2 = 0;             // stage-ring positions of the P1 / P2 stage (BWD reads coefficients from the stage)
-        int e1 = 0, e2 = 0;             // ering slots
-        for (int it = 0; it < n_i + kFsSkew; ++it) {
+        // one thread base (sample column q*32 + lane of every [..][128]-float row) + per-purpose constants
+        const uint32_t tb = base + (uint32_t)(q * 32 + lane) * 4;
+        const uint32_t zp_base = tb + kOffZpart + (uint32_t)jh * 512;                    // + zs * 1024
+        const uint32_t zr_base = tb + kOffZrecv;                                         // + zs * 4096 + rank * 512
+        const uint32_t er_base = tb + kOffEring + (uint32_t)jh * 2048;                   // + eslot * 4096 + jj * 512
+        const uint32_t co_base = base + kOffStages + kFsOperandBytes + (uint32_t)((q * 8 + jh * 4) * kLanes + lane) * 4;   // + stage * kStageBytes + jj * 128
+        uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * 64);
+        asm volatile("mov.b32 %0, %0;" : "+r"(lane_base));          // pin (same reason)
+        // the coefficient row this warp stores in P2 (c^r or beta^r of (tile, i, j0 + jj)): advances one input capsule per stage
+        uintptr_t cptr = reinterpret_cast<uintptr_t>(p.coef_out) + ((((size_t)(tvalid ? tile : 0) * p.N + i_begin) * (p.JG * 8) + j0) * kLanes + lane) * 4;
+        const uintptr_t cstep = (uintptr_t)p.JG * 8 * kLanes * 4;
+        uint32_t st1 = 0, st2 = 0;                      // BWD: byte offset of the P1 / P2 stage in the ring
+        uint32_t sb2 = 0;                               // BWD: smem_empty barrier offset of the P2 stage
+        const uint32_t st_end = (uint32_t)ns * kStageBytes;
+        uint32_t er1 = 0, er2 = 0;                      // ering slot offsets
+        const int n_it = n_i + kFsSkew;
+        for (int it = 0; it < n_it; ++it) {
             if (it < n_i) {
                 // ---------------- P1(it): logits / dc, partial normaliser ----------------
-                const int n = it, t = n & (kFsAccum - 1);
-                mbar_wait_i(tmem_full + 8 * t, (n >> 2) & 1);
+                const uint32_t t = (uint32_t)it & (kFsAccum - 1), zs = (uint32_t)it & (kFsZSlots - 1);
+                mbar_wait_i(base + kOffTmemFull + 8 * t, ((uint32_t)it >> 2) & 1);
                 tc_fence_after();
-                float uh[64];
-                tmem_ld64(lane_base + (uint32_t)(t * 128), uh);
                 float z = 0.f;
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                for (int hh = 0; hh < 2; ++hh) {
+                    float uh[32];
+                    tmem_ld32(lane_base + t * 128 + hh * 32, uh);
 #pragma unroll
-                    for (int d = 0; d < 16; d += 4) {
-                        ffma2(d0, d1, uh[jj * 16 + d], uh[jj * 16 + d + 1], X[jj][d], X[jj][d + 1]);
-                        ffma2(d2, d3, uh[jj * 16 + d + 2], uh[jj * 16 + d + 3], X[jj][d + 2], X[jj][d + 3]);
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        const int jj = hh * 2 + j2;
+                        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 16; d += 4) {
+                            ffma2(d0, d1, uh[j2 * 16 + d], uh[j2 * 16 + d + 1], X[jj][d], X[jj][d + 1]);
+                            ffma2(d2, d3, uh[j2 * 16 + d + 2], uh[j2 * 16 + d + 3], X[jj][d + 2], X[jj][d + 3]);
+                        }
+                        const float dot = (d0 + d1) + (d2 + d3);
+                        float keep;
+                        if (!BWD) {
+                            keep = ex2_approx(fminf(dot, lim[jj]));
+                            z += keep;
+                        } else {
+                            keep = dot;
+                            z = fmaf(lds_f32(co_base + st1 + jj * 128), dot, z);
+                        }
+                        sts_f32(er_base + er1 + jj * 512, keep);
                     }
-                    const float dot = (d0 + d1) + (d2 + d3);
-                    float keep;
-                    if (!BWD) {
-                        keep = (j0 + jj < p.C) ? ex2_approx(fminf(dot, 120.f)) : 0.f;
-                        z += keep;
-                    } else {
-                        keep = dot;
-                        float c = 0.f;
-                        if (tvalid && j0 + jj < p.C) c = lds_f32(stages + (uint32_t)s1 * kStageBytes + my_coef + jj * 128);
-                        z = fmaf(c, dot, z);
-                    }
-                    sts_f32(my_ering + (uint32_t)e1 * 4096 + jj * 128, keep);
                 }
-                sts_f32(my_zpart + (uint32_t)(n & (kFsZSlots - 1)) * 1024, z);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(zlocal + 8 * (n & (kFsZSlots - 1)));
-                if (++s1 == ns) s1 = 0;
-                if (++e1 == kFsSkew + 1) e1 = 0;
+                if (!no_xchg) {
+                    sts_f32(zp_base + zs * 1024, z);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(base + kOffZlocal + 8 * zs);
+                }
+                if (BWD) { st1 += kStageBytes; if (st1 == st_end) st1 = 0; }
+                er1 += 4096; if (er1 == (kFsSkew + 1) * 4096) er1 = 0;
             }
             if (it >= kFsSkew) {
                 // ---------------- P2(it - skew): normalise, store, accumulate ----------------
-                const int m = it - kFsSkew, t = m & (kFsAccum - 1);
-                const int i = i_begin + m;
-                const uint32_t slot = (uint32_t)m & (kFsZSlots - 1);
-                mbar_wait_i(zfull + 8 * slot, ((uint32_t)m >> 2) & 1);
-                float Z = 0.f;
-                for (int r = 0; r < p.JG; ++r) Z += lds_f32(my_zrecv + (slot * kFsMaxCluster + (uint32_t)r) * 512);
+                const uint32_t m = (uint32_t)(it - kFsSkew), t = m & (kFsAccum - 1), zs = m & (kFsZSlots - 1);
+                float Z = 1.f;
+                if (!no_xchg) {
+                    mbar_wait_i(base + kOffZfull + 8 * zs, (m >> 3) & 1);
+                    const uint32_t zr = zr_base + zs * 4096;
+                    float zz[kFsMaxCluster];
+#pragma unroll
+                    for (int r = 0; r < kFsMaxCluster; ++r) zz[r] = lds_f32(zr + r * 512);
+                    Z = ((zz[0] + zz[1]) + (zz[2] + zz[3])) + ((zz[4] + zz[5]) + (zz[6] + zz[7]));    // fixed order: same bits in every CTA
+                }
                 float f[4];
+                const float rz = BWD ? 0.f : rcp_approx(Z);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const float keep = lds_f32(my_ering + (uint32_t)e2 * 4096 + jj * 128);
+                    const float keep = lds_f32(er_base + er2 + jj * 512);
                     if (!BWD) {
-                        f[jj] = keep * rcp_approx(Z);
+                        f[jj] = keep * rz;
                     } else {
-                        float c = 0.f, bp = 0.f;
-                        if (tvalid && j0 + jj < p.C) {
-                            c = lds_f32(stages + (uint32_t)s2 * kStageBytes + my_coef + jj * 128);
-                            if (p.beta_in != nullptr) bp = lds_f32(stages + (uint32_t)s2 * kStageBytes + kFsCoefBytes + my_coef + jj * 128);
-                        }
+                        const float c = lds_f32(co_base + st2 + jj * 128);
+                        const float bp = has_beta ? lds_f32(co_base + st2 + kFsCoefBytes + jj * 128) : 0.f;
                         f[jj] = fmaf(c, keep - Z, bp);
                     }
-                    if (tvalid && j0 + jj < p.C && p.coef_out != nullptr)
-                        p.coef_out[(((size_t)tile * p.N + i) * p.C + j0 + jj) * kLanes + lane] = f[jj];
+                }
+                if (do_store) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) reinterpret_cast<float*>(cptr)[jj * kLanes] = f[jj];
                 }
                 tc_fence_after();
-                float uh[64];
-                tmem_ld64(lane_base + (uint32_t)(t * 128), uh);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(tmem_empty + 8 * t);
-                    if (BWD) mbar_arrive(smem_empty + 8 * s2);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float uh[32];
+                    tmem_ld32(lane_base + t * 128 + hh * 32, uh);
+                    if (hh == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(base + kOffTmemEmpty + 8 * t);               // accumulator t may be overwritten
+                            if (BWD) mbar_arrive(base + kOffSmemEmpty + sb2);        // and the coefficient rows of the P2 stage
+                        }
+                    }
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        const int jj = hh * 2 + j2;
+#pragma unroll
+                        for (int d = 0; d < 16; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], uh[j2 * 16 + d], uh[j2 * 16 + d + 1]);
+                    }
                 }
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int d = 0; d < 16; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], uh[jj * 16 + d], uh[jj * 16 + d + 1]);
-                if (++s2 == ns) s2 = 0;
-                if (++e2 == kFsSkew + 1) e2 = 0;
+                cptr += cstep;
+                if (BWD) { st2 += kStageBytes; sb2 += 8; if (st2 == st_end) { st2 = 0; sb2 = 0; } }
+                er2 += 4096; if (er2 == (kFsSkew + 1) * 4096) er2 = 0;
             }
         }
         if (tvalid) {
@@ -333,11 +395,11 @@ __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
-    cluster_sync_all();                      // no CTA leaves while a peer's bulk copy may still read its shared memory
+    cluster_sync_all();                      // no CTA leaves while a peer's stores may still be on their way to it
 }
 
 // couplings in the lane-tile layout [nbt][N][C][32] -> public [B][N][C] (tests and callers that ask for c_out)
-__global__ void k_coef_public(const float* __restrict__ coef, float* __restrict__ c_pub, int B, int N, int C, int nbt) {
+__global__ void k_coef_public(const float* __restrict__ coef, float* __restrict__ c_pub, int B, int N, int C, int CS, int nbt) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)nbt * N * kLanes) return;
     const int lane = (int)(idx & 31);
@@ -345,7 +407,7 @@ __global__ void k_coef_public(const float* __restrict__ coef, float* __restrict_
     const long b = (ti / N) * kLanes + lane;
     if (b >= B) return;
     const int i = (int)(ti % N);
-    const float* src = coef + (size_t)ti * C * kLanes + lane;
+    const float* src = coef + (size_t)ti * CS * kLanes + lane;
     float* dst = c_pub + ((size_t)b * N + i) * C;
     for (int j = 0; j < C; ++j) dst[j] = src[(size_t)j * kLanes];
 }
@@ -356,7 +418,7 @@ ClusterCap g_cap[2];
 template <bool BWD>
 int launch_t(const Plan& pl, const FusedParams& fp, int IS, cudaStream_t st) {
     auto kern = k_sweep_fused<BWD>;
-    const size_t smem = (size_t)fp.ns * fs_stage_bytes(BWD) + kFsFixedBytes;
+    const size_t smem = (size_t)kOffStages + (size_t)fp.ns * fs_stage_bytes(BWD);
     CAPS_SET_SMEM(kern, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(fp.JG, IS, cdiv(pl.nbt, 4));
@@ -374,16 +436,17 @@ int launch_t(const Plan& pl, const FusedParams& fp, int IS, cudaStream_t st) {
 
 int fs_stages(bool bwd) {
     int ns = bwd ? 7 : 8;
-    while ((size_t)ns * fs_stage_bytes(bwd) + kFsFixedBytes > 227 * 1024) --ns;
+    while ((size_t)kOffStages + (size_t)ns * fs_stage_bytes(bwd) > 227 * 1024) --ns;
     return ns;
 }
 
 }  // namespace
 
+int g_fs_dbg = 0;
+
 // D == 16 (after padding), 8 capsules per CTA, one cluster of ceil(C/8) <= 8 CTAs per (128 samples, i range)
-bool fused_supported(const Plan& pl) {
-    return pl.use_tc && pl.DP == 16 && pl.Reff > 1 && cdiv(pl.C, 8) <= kFsMaxCluster;
-}
+bool fused_shape_ok(int C, int DP, bool tc_ok) { return tc_ok && DP == 16 && cdiv(C, 8) <= kFsMaxCluster; }
+bool fused_supported(const Plan& pl) { return pl.use_tc && pl.Reff > 1 && fused_shape_ok(pl.C, pl.DP, pl.tc_ok); }
 
 // clusters of `jg` CTAs the device can run at once (GPC granularity: not simply SMs / jg)
 int fused_cluster_capacity(int jg, bool bwd) {
@@ -392,7 +455,7 @@ int fused_cluster_capacity(int jg, bool bwd) {
     std::atomic<int>& slot = g_cap[bwd ? 1 : 0].n[dev][jg];
     int n = slot.load(std::memory_order_relaxed);
     if (n > 0) return n;
-    const size_t smem = (size_t)fs_stages(bwd) * fs_stage_bytes(bwd) + kFsFixedBytes;
+    const size_t smem = (size_t)kOffStages + (size_t)fs_stages(bwd) * fs_stage_bytes(bwd);
     const void* kern = bwd ? reinterpret_cast<const void*>(k_sweep_fused<true>) : reinterpret_cast<const void*>(k_sweep_fused<false>);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg = {};
@@ -439,13 +502,14 @@ int launch_sweep_fused(const Plan& pl, bool bwd, const float* ua, const float* w
     fp.N = pl.N; fp.C = pl.C; fp.JG = cdiv(pl.C, 8); fp.nbt = pl.nbt;
     fp.i_per_split = cdiv(cdiv(pl.N, IS), 4) * 4;
     fp.ns = fs_stages(bwd);
+    fp.dbg = g_fs_dbg;
     if (cdiv(pl.N, fp.i_per_split) != IS) return fail(CAPS_E_BADARG, "fused sweep: %d splits do not tile N=%d", IS, pl.N);
     return bwd ? launch_t<true>(pl, fp, IS, st) : launch_t<false>(pl, fp, IS, st);
 }
 
-int launch_coef_public(const Plan& pl, const float* coef, float* c_pub, cudaStream_t st) {
+int launch_coef_public(const Plan& pl, const float* coef, int CS, float* c_pub, cudaStream_t st) {
     const long n = (long)pl.nbt * pl.N * kLanes;
-    k_coef_public<<<cdiv(n, 256), 256, 0, st>>>(coef, c_pub, pl.B, pl.N, pl.C, pl.nbt);
+    k_coef_public<<<cdiv(n, 256), 256, 0, st>>>(coef, c_pub, pl.B, pl.N, pl.C, CS, pl.nbt);
     LAUNCH_CHECK();
     return 0;
 }

@@ -31,7 +31,14 @@ t0 = time.time()
 with torch.no_grad():
     v, c = m.dynamic_routing(ut, Wt, R, return_couplings=True)
 torch.cuda.synchronize()
-print('dims', (B, N, C, D, R), 'fused', fused, 'fwd ok %.2fs' % (time.time() - t0), 'v', rel(v.cpu().numpy(), ref['v']), 'c', rel(c.cpu().numpy(), ref['c']), flush=True)
+vn, cn = v.cpu().numpy(), c.cpu().numpy()
+print('dims', (B, N, C, D, R), 'fused', fused, 'fwd ok %.2fs' % (time.time() - t0), 'v', rel(vn, ref['v']), 'c', rel(cn, ref['c']), flush=True)
+ev = np.abs(vn - ref['v']).reshape(B, -1).max(1)
+worst = np.argsort(-ev)[:8]
+print('   worst samples (b, err, |v|max):', [(int(b), float('%.2e' % ev[b]), float('%.3f' % np.abs(ref['v'][b]).max())) for b in worst], 'median err %.2e' % np.median(ev), flush=True)
+ec = np.abs(cn - ref['c'])
+bi = np.unravel_index(np.argmax(ec), ec.shape)
+print('   worst c at (b,i,j)', bi, 'err %.2e' % ec[bi], 'ref %.4e' % ref['c'][bi], 'sum_j c -1: %.2e' % np.abs(cn.sum(-1) - 1).max(), flush=True)
 v, loss = m.routing_margin_loss(ut, Wt, yt, R)
 loss.backward()
 torch.cuda.synchronize()
