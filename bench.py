@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 N_NODES, N_CAPS, IN_C, OUT_C, N_ITER = 1152, 43, 8, 16, 3
 METRIC = 'capsule-routing samples/sec fwd+bwd'
 UNIT = 'samples/s'
-KCLASS = ['layout', 'pass_A0', 'pass_L', 'pass_A', 'squash', 'softmax', 'grad', 'du_reduce', 'loss', 'other', 'fused_sweep']
+KCLASS = ['layout', 'pass_A0', 'pass_L', 'pass_A', 'squash', 'softmax', 'grad', 'du_reduce', 'loss', 'other', 'fused_sweep', 'c1_kernels']
 
 
 def workload_name(batch):
@@ -196,6 +196,8 @@ def main_gpu(args, rank, world, device):
     from cs231_capsule_yolo_traffic_sign_detection_b200 import _cabi
     L = _cabi.lib()                       # raises if the CUDA library is missing (no fallback)
     B, N, C, K, D, R = args.batch, N_NODES, N_CAPS, IN_C, OUT_C, N_ITER
+    if args.scaling == 'strong':
+        B = max(128, (args.batch // world) // 128 * 128)      # fixed GLOBAL batch, sharded
     if args.spt:
         _cabi.set_tuning('spt', args.spt)
     if args.isplit:
@@ -217,7 +219,12 @@ def main_gpu(args, rank, world, device):
     y = y_host.to(device)
     v = torch.empty(B, C, D, device=device)
     du = torch.empty(B, N, K, device=device)
-    dW = torch.empty_like(W)
+    # the product's data-parallel plumbing: dW lives in the flat gradient bucket the collective reduces (parallel.GradBucket)
+    Wparam = torch.nn.Parameter(W)
+    bucket = pkg.GradBucket([Wparam])
+    dW = Wparam.grad
+    dw_ready = torch.cuda.Event()
+    dw_ready.record()                      # materialises the cudaEvent_t handle
     loss = torch.empty((), device=device)
     lscr = torch.empty(_cabi.MARGIN_SCRATCH_FLOATS, device=device)
     nbytes = L.caps_route_workspace_bytes(B, N, C, K, D, R, 1)
@@ -228,12 +235,16 @@ def main_gpu(args, rank, world, device):
     def step_device():
         _cabi.check(L.caps_route_forward(P(u), P(W), P(v), None, P(ws), nbytes, B, N, C, K, D, R, 1, stream), 'fwd')
         _cabi.check(L.caps_margin_loss(P(v), P(y), 1.0 / B, P(loss), None, P(lscr), B, C, D, stream), 'loss')
-        _cabi.check(L.caps_route_backward(P(u), P(W), None, P(y), 1.0 / B, None, P(du), P(dW), P(ws), nbytes,
-                                          B, N, C, K, D, R, stream), 'bwd')
+        bucket.wait()                      # the previous step's all-reduce must be done before dW is rewritten (stream-level)
+        _cabi.check(L.caps_route_backward_ev(P(u), P(W), None, P(y), 1.0 / B, None, P(du), P(dW), P(ws), nbytes,
+                                             B, N, C, K, D, R, stream, dw_ready.cuda_event), 'bwd')
         if world > 1:
-            dist.all_reduce(dW)            # data-parallel gradient average (sum here; scale folded into lr)
+            # gradient AVERAGE across ranks on the bucket's comm stream, gated by the event the backward records right
+            # behind the kernel that completes dW: overlaps the du reduction and the next step's forward
+            bucket.allreduce_async(dw_ready, average=True)
 
     def barrier():
+        bucket.wait()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -245,6 +256,7 @@ def main_gpu(args, rank, world, device):
         e0.record()
         for _ in range(steps):
             fn()
+        bucket.wait()                      # the last step's all-reduce belongs to the timed region
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -279,12 +291,17 @@ def main_gpu(args, rank, world, device):
     loss_val = float(loss)
 
     # ---- end to end through the host-buffer C-ABI call ----------------------------------------
-    host = pkg.HostStep(B, N, C, K, D, R, device=device)
+    # caps_host_pipe_*: every step copies ITS inputs host -> device (pinned memory) and its loss device -> host; the copy
+    # of step n+1 is submitted before step n runs, so it overlaps the kernels (two device input slots)
+    host = pkg.HostPipe(B, N, C, K, D, R, device=device)
+    host.submit(u_host, y_host)
 
     def step_host():
-        host(u_host, y_host, W, dW)
+        host.submit(u_host, y_host)        # next step's inputs: H2D on the pipe's copy stream
+        bucket.wait()
+        host.step(W, dW, dw_ready_event=dw_ready)
         if world > 1:
-            dist.all_reduce(dW)
+            bucket.allreduce_async(dw_ready, average=True)
     for _ in range(max(1, min(args.warmup, 3))):
         step_host()
     ms_e2e, _, _ = timed(step_host, args.steps)
@@ -344,63 +361,66 @@ def main_gpu(args, rank, world, device):
 
     per_class = {KCLASS[i]: {'ms_per_step': ms_cls[i] / args.steps, 'launches_per_step': n_cls[i] / args.steps}
                  for i in range(len(KCLASS)) if n_cls[i]}
-    # --- the dominant kernel (largest share of the timed region) gets the `roofline` object ---------
-    n_pass = sum(n_cls[i] for i in (1, 2, 3, 10))
-    ms_pass = sum(ms_cls[i] for i in (1, 2, 3, 10))
-    ms_grad, n_grad = ms_cls[6], max(n_cls[6], 1)
-    # algorithmic work of ONE launch:
-    #   pass kernel : flops = B (2 NCKD + 2 NCD)   bytes = B (4 NK + 4 NC) + 4 NCKD
-    #                 (u read + one [B,N,C] coefficient array read or written + W read once)
-    #   grad kernel : flops = B (4 NCKD + 2 (2R-1) NCD)   bytes = B (4 (2R-2) NC + 8 NK) + 8 NCKD
-    #                 (2R-2 coefficient arrays + u read, du written, W read, dW written)
-    pass_flops = B * (2.0 * N * C * K * D + 2.0 * N * C * D)
-    pass_bytes = B * (4.0 * N * K + 4.0 * N * C) + 4.0 * N * C * K * D
-    grad_flops = B * (4.0 * N * C * K * D + 2.0 * (2 * R - 1) * N * C * D)
-    grad_bytes = B * (4.0 * (2 * R - 2) * N * C + 8.0 * N * K) + 8.0 * N * C * K * D
-    if ms_grad >= ms_pass:
-        dom, dom_ms, dom_bytes, dom_flops, dom_n = 'k_grad_mma (dW/du, mma.sync 3xTF32)', ms_grad / n_grad, grad_bytes, grad_flops, n_grad
-        dom_share = ms_grad / ms_prof
-    else:
-        dom, dom_ms, dom_bytes, dom_flops, dom_n = 'k_pass_tc (u_hat sweep, tcgen05 3xTF32)', ms_pass / max(n_pass, 1), pass_bytes, pass_flops, n_pass
-        dom_share = ms_pass / ms_prof
-    ach_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
-    # measured DRAM traffic of that kernel (one `ncu --set full` capture, committed under profiles/), per launch
-    traffic = None
+    # --- per-kernel-class algorithmic work of ONE launch ------------------------------------
+    #   uniform / L / A sweep : flops B (2 NCKD + 2 NCD)        bytes B (4 NK + 4 NC) + 4 NCKD
+    #   fused sweep           : flops B (2 NCKD + 4 NCD)        bytes B (4 NK + a 4 NC) + 4 NCKD, a = [B,N,C] arrays it
+    #                           touches: 1 (forward: c written), 2 (top backward: c read, beta written), 3 (inner backward)
+    #   gradient sweep        : flops B (4 NCKD + 2 (2R-1) NCD) bytes B (4 (2R-2) NC + 8 NK) + 8 NCKD
+    #   single-capsule kernels: bytes B 12 NK + 12 NKD (u read twice, du written; W read twice, dW written)
+    Re = 1 if C == 1 else R
+    cls_bytes, cls_flops = {}, {}
+    sweep_flops = B * (2.0 * N * C * K * D + 2.0 * N * C * D)
+    for c in (1, 2, 3):
+        cls_bytes[c] = B * (4.0 * N * K + 4.0 * N * C) + 4.0 * N * C * K * D
+        cls_flops[c] = sweep_flops
+    arrays_fused = (Re - 1) * 1 + 2 + 3 * max(Re - 2, 0)                        # per step, over its 2 (Re - 1) launches
+    cls_bytes[10] = (2 * (Re - 1) * (B * 4.0 * N * K + 4.0 * N * C * K * D) + arrays_fused * B * 4.0 * N * C) / max(2 * (Re - 1), 1)
+    cls_flops[10] = B * (2.0 * N * C * K * D + 4.0 * N * C * D)
+    cls_bytes[6] = B * (4.0 * (2 * Re - 2) * N * C + 8.0 * N * K) + 8.0 * N * C * K * D
+    cls_flops[6] = B * (4.0 * N * C * K * D + 2.0 * (2 * Re - 1) * N * C * D)
+    cls_bytes[11] = (B * 12.0 * N * K + 12.0 * N * K * D) / 3.0                    # three launches per step share it
+    cls_flops[11] = B * 6.0 * N * K * D / 3.0
+    names = {1: 'k_pass_tc<uniform> (u_hat sweep, tcgen05 3xTF32, TMEM-accumulated)', 2: 'k_pass_tc<L>', 3: 'k_pass_tc<A>',
+             6: 'k_grad_mma (dW/du sweep, mma.sync 3xTF32)' if C >= 7 and D >= 9 else 'k_grad (dW/du sweep, fp32 FMA)',
+             10: 'k_sweep_fused (logits -> softmax -> weighted sum in one sweep; tcgen05 3xTF32 + DSMEM exchange)',
+             11: 'k_c1_fwd / k_c1_bwd / k_c1_reduce (single class capsule: skinny GEMM + squash)'}
+    traffic_by_class = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))
-        if tj.get('batch') == B and tj.get('n_nodes') == N:
-            pref = 'k_grad_mma<5' if dom.startswith('k_grad') else 'k_pass_tc<1>'
-            traffic = [v['dram_bytes_per_launch'] for k, v in tj['kernels'].items() if k.startswith(pref)][0]
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))
+        if tj.get('batch') == B and tj.get('n_nodes') == N and tj.get('n_caps') == C:
+            traffic_by_class = {int(k): v for k, v in tj.get('dram_bytes_per_launch_by_class', {}).items()}
     except Exception:
         pass
-    roofline = {'bound': 'hbm', 'kernel': '%s; %d launches/step' % (dom, dom_n // args.steps),
-                'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
-                'traffic': traffic, 'peak_source': hbm_src, 'share_of_step': dom_share,
-                'algorithmic_tflops': dom_flops / (dom_ms * 1e-3) / 1e12,
-                'note': 'neither HBM nor the dense tensor peak binds this kernel: the contraction is K=8 wide and needs '
-                        'fp32-grade accuracy (3xTF32), so the limit is shared-memory / issue bandwidth; see DESIGN.md section 5'}
-    ach_tf = pass_flops / (ms_pass / max(n_pass, 1) * 1e-3) / 1e12
-    roofline_fp32 = {'bound': 'fp32_fma', 'kernel': 'k_pass_tc', 'achieved': ach_tf, 'peak': fma_peak, 'unit': 'TFLOP/s',
-                     'frac': ach_tf / fma_peak,
-                     'peak_source': 'measured live: caps_fma_peak (register-operand FFMA chains); a fraction above 1 means '
-                                    'the tcgen05 path beats what any fp32-FMA kernel could do',
-                     'share_of_step': ms_pass / ms_prof,
-                     'hbm_gbs': pass_bytes / (ms_pass / max(n_pass, 1) * 1e-3) / 1e9}
-    # the HBM-bound kernels of the step: softmax forward (one [B,N,C] array read + written, R-1 launches) and
-    # softmax backward (c, dc [, beta carry] read, beta written: 3 arrays for the last iteration, 4 for the others)
-    roofline_softmax = None
-    try:
-        Re = 1 if C == 1 else R
-        n_arrays = 2 * (Re - 1) + 3 * (Re - 1) + max(Re - 2, 0)
-        if n_cls[5] and n_arrays:
-            sm_bytes = n_arrays * 4.0 * B * N * C                      # per step
-            sm_gbs = sm_bytes / (ms_cls[5] / args.steps * 1e-3) / 1e9
-            roofline_softmax = {'bound': 'hbm', 'kernel': 'k_softmax_reg + k_softmax_bwd_staged; %d launches/step' % (n_cls[5] // args.steps),
-                                'achieved': sm_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': sm_gbs / hbm_peak,
-                                'peak_source': hbm_src + ' (a copy bandwidth: read-mostly kernels can exceed it)',
-                                'share_of_step': ms_cls[5] / ms_prof}
-    except Exception:
-        roofline_softmax = None
+
+    def roof(c):
+        if not n_cls[c] or c not in cls_bytes:
+            return None
+        ms1 = ms_cls[c] / n_cls[c]
+        gbs = cls_bytes[c] / (ms1 * 1e-3) / 1e9
+        return {'bound': 'hbm', 'kernel': '%s; %d launches/step' % (names.get(c, KCLASS[c]), n_cls[c] // args.steps),
+                'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                'traffic': traffic_by_class.get(c), 'peak_source': hbm_src, 'share_of_step': ms_cls[c] / ms_prof,
+                'ms_per_launch': ms1, 'algorithmic_bytes_per_launch': cls_bytes[c],
+                'algorithmic_tflops': cls_flops[c] / (ms1 * 1e-3) / 1e12}
+    cand = [c for c in cls_bytes if n_cls[c]]
+    dom = max(cand, key=lambda c: ms_cls[c])
+    roofline = roof(dom)
+    binds = {6: 'shared-memory pipe and issue slots, not HBM and not the tensor pipe (ncu, profiles/): both products have one side '
+                'only 8 wide and need fp32-grade accuracy (3xTF32), the G operand is built per sample on the FMA pipe and has to '
+                'cross shared memory to reach both fragment layouts; tools/probe_tc2.cu + DESIGN.md 3.3 say why tcgen05 does not help',
+             10: 'issue slots of the 8 epilogue warps (ncu: ~200 instructions per warp and input capsule at ~40 % issue '
+                 'efficiency with two warps per scheduler); tensor pipe ~20 % busy, DRAM < 10 %',
+             11: 'HBM (u is read twice and du written once; nothing else is large)'}
+    roofline['binds'] = binds.get(dom, 'see DESIGN.md section 5')
+    roofline_other = {KCLASS[c]: roof(c) for c in cand if c != dom}
+    # tensor-pipe view of the sweeps: 3xTF32 issues 3 MMAs per algorithmic one; tf32 dense peak = half the measured bf16 peak
+    tf32_peak = float(peaks.get('bf16_tflops', 1590.0)) / 2.0
+    for c in (1, 10):
+        r_ = roofline if c == dom else roofline_other.get(KCLASS[c])
+        if r_:
+            mma_tf = 3.0 * B * 2.0 * N * C * K * D * (1 if c == 1 else 1) / (r_['ms_per_launch'] * 1e-3) / 1e12
+            r_['tensor'] = {'issued_tflops_3xtf32': mma_tf, 'peak': tf32_peak, 'frac': mma_tf / tf32_peak,
+                            'peak_source': 'MEASURED_PEAKS.json bf16_tflops / 2 (tf32 runs at half the bf16 rate)'}
     step_tf = flops_per_sample() * B / (ms_per_step * 1e-3) / 1e12
     step_gbs = hbm_bytes_per_step(B) / (ms_per_step * 1e-3) / 1e9
     roofline_step = {'algorithmic_tflops': step_tf, 'frac_of_fp32_peak': step_tf / fma_peak,
@@ -410,7 +430,7 @@ def main_gpu(args, rank, world, device):
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(B), 'n_nodes': N, 'n_caps': C, 'in_C': K, 'out_C': D, 'n_iter': R,
                    'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
@@ -419,10 +439,10 @@ def main_gpu(args, rank, world, device):
                    'loss': loss_val},
         'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': host.h2d_bytes,
                 'd2h_bytes_per_step': host.d2h_bytes, 'ms_per_step': ms_e2e / args.steps,
-                'api': 'caps_route_step_host (pinned host u,y -> device; loss -> host)'},
+                'api': 'caps_host_pipe_submit/step (pinned host u,y -> device every step, prefetched one step ahead; loss -> host)'},
         'gpu_launches': int(launches),
         'clocks': clk,
-        'roofline': roofline, 'roofline_fp32': roofline_fp32, 'roofline_softmax': roofline_softmax, 'roofline_step': roofline_step,
+        'roofline': roofline, 'roofline_other_kernels': roofline_other, 'roofline_step': roofline_step,
         'kernel_ms_per_step': per_class, 'profiled_ms_per_step': ms_prof / args.steps,
         'cpu_baseline': cpu,
         'eager_b200': eager,
@@ -535,6 +555,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=8192, help='per-GPU batch (weak scaling)')
     ap.add_argument('--cpu-sample', type=int, default=64, help='micro-batch of the CPU baseline')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak (default): --batch per GPU; strong: --batch is the global batch, sharded over the GPUs')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-reference-on-GPU leg')
     ap.add_argument('--eager-batch', type=int, default=256, help='micro-batch of the eager reference on the GPU')

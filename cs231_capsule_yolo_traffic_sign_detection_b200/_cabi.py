@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('CAPS_ROUTING_LIB') or os.path.join(HERE, 'libcaps_routing.so')   # env override: A/B experiments
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MARGIN_SCRATCH_FLOATS = 2048
 
 # every symbol include/caps_routing.h declares: name -> (restype, argtypes)
@@ -21,6 +21,7 @@ SYMBOLS = {
     'caps_route_workspace_bytes': (_sz, [_i] * 7),
     'caps_route_forward': (_i, [_vp, _vp, _vp, _vp, _vp, _sz] + [_i] * 7 + [_vp]),
     'caps_route_backward': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz] + [_i] * 6 + [_vp]),
+    'caps_route_backward_ev': (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz] + [_i] * 6 + [_vp, _vp]),
     'caps_margin_loss': (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'caps_squash': (_i, [_vp, _vp, _l, _i, _vp]),
     'caps_squash_backward': (_i, [_vp, _vp, _vp, _l, _i, _vp]),
@@ -31,6 +32,11 @@ SYMBOLS = {
     'caps_dark_loss': (_i, [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'caps_route_step_host_scratch_bytes': (_sz, [_i] * 6),
     'caps_route_step_host': (_i, [_vp] * 8 + [_sz] + [_i] * 6 + [_vp]),
+    'caps_host_pipe_scratch_bytes': (_sz, [_i] * 6),
+    'caps_host_pipe_create': (_i, [_vp, _vp, _sz] + [_i] * 6),
+    'caps_host_pipe_submit': (_i, [_vp, _vp, _vp]),
+    'caps_host_pipe_step': (_i, [_vp] * 7),
+    'caps_host_pipe_destroy': (_i, [_vp]),
     'caps_set_tuning': (_i, [ctypes.c_char_p, _i]),
     'caps_kernel_launch_count': (_l, []),
     'caps_profile_collect': (_i, [_vp, _vp, _i]),

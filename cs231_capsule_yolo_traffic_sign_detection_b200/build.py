@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 INCLUDE = os.path.join(ROOT, 'include')
 LIB = os.path.join(HERE, 'libcaps_routing.so')
 OBJ_DIR = os.path.join(HERE, 'build')
-UNITS = ['caps_api.cu', 'caps_pass.cu', 'caps_grad.cu', 'caps_pass_tc.cu', 'caps_grad_mma.cu', 'caps_sweep_fused.cu']
+UNITS = ['caps_api.cu', 'caps_pass.cu', 'caps_grad.cu', 'caps_pass_tc.cu', 'caps_grad_mma.cu', 'caps_sweep_fused.cu', 'caps_c1.cu']
 HEADERS = [os.path.join(CSRC, 'caps_kernels.cuh'), os.path.join(CSRC, 'caps_internal.h'), os.path.join(CSRC, 'caps_tc_common.cuh'),
            os.path.join(INCLUDE, 'caps_routing.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',

@@ -330,6 +330,51 @@ class CapsuleLayer(nn.Module):
         return v.view(B, 1, C, 1, D), loss
 
 
+class HostPipe:
+    """Double-buffered end-to-end call (caps_host_pipe_*): `submit` starts the host->device copy of a batch on an
+    internal stream, `step` runs forward + margin loss + fused backward on the batch submitted first and returns the
+    loss on the host.  Submitting batch n+1 before stepping batch n hides the copy under the kernels."""
+
+    def __init__(self, B, N, C, K, D, n_iter, device='cuda'):
+        import ctypes
+        L = _cabi.lib()
+        self.dims = (B, N, C, K, D, n_iter)
+        nbytes = L.caps_host_pipe_scratch_bytes(B, N, C, K, D, n_iter)
+        if nbytes == 0:
+            raise RuntimeError('unsupported dims %s' % (self.dims,))
+        self.device = torch.device(device)
+        self.scratch = torch.empty((nbytes,), device=self.device, dtype=torch.uint8)
+        self.loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+        self._pipe = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(L.caps_host_pipe_create(ctypes.byref(self._pipe), _ptr(self.scratch), nbytes, B, N, C, K, D, n_iter),
+                        'caps_host_pipe_create')
+        self.h2d_bytes = B * N * K * 4 + B * 8
+        self.d2h_bytes = 4
+
+    def submit(self, u_host, y_host):
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().caps_host_pipe_submit(self._pipe, _ptr(u_host), _ptr(y_host)), 'caps_host_pipe_submit')
+
+    def step(self, W_dev, dW_dev, v_host=None, dw_ready_event=None):
+        ev = None if dw_ready_event is None else dw_ready_event.cuda_event
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().caps_host_pipe_step(self._pipe, _ptr(W_dev), _ptr(dW_dev), _ptr(self.loss_host), _ptr(v_host),
+                                                        _stream(), ev), 'caps_host_pipe_step')
+        return self.loss_host
+
+    def close(self):
+        if self._pipe:
+            _cabi.lib().caps_host_pipe_destroy(self._pipe)
+            self._pipe = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostStep:
     """End-to-end call with HOST buffers through caps_route_step_host: u, y come from (pinned)
     host memory every step, the loss (and optionally v / du) go back to the host; W and dW stay

@@ -45,6 +45,7 @@ int g_tune_gradmma = 1;  // 1 = mma.sync gradient kernel where it applies (D == 
 int g_tune_hostmb = 0;   // caps_route_step_host: 0 = auto (3 micro-batches from B >= 2048), 1 = single batch
 int g_tune_sbstaged = 1;  // softmax backward through the staged kernel (16 < C <= 48)
 int g_tune_tc = 1;       // 1 = use the tcgen05 pass kernel where it applies, 0 = FFMA kernel only
+int g_tune_c1 = 1;       // 1 = dedicated kernels for one class capsule (the DarkCapsuleNet head)
 int g_tune_fused = 1;    // 1 = cluster-fused sweep (logits -> softmax -> weighted sum in one kernel) where it applies
 
 // ---- forward records ---------------------------------------------------------------------------
@@ -52,7 +53,7 @@ int g_tune_fused = 1;    // 1 = cluster-fused sweep (logits -> softmax -> weight
 // operand copies the workspace now holds); caps_route_backward looks the record up, returns CAPS_E_STATE when there
 // is none / the dims differ / the forward ran without with_grad, and replays the recorded engine choices instead of
 // reading the tuning knobs again.  Host-side bookkeeping only (mutex-guarded, fixed size, oldest entry recycled).
-struct FwdRecord { const void* ws; int dev, B, N, C, K, D, R; bool with_grad, use_tc, fused; unsigned long stamp; };
+struct FwdRecord { const void* ws; int dev, B, N, C, K, D, R; bool with_grad, use_tc, fused, c1; unsigned long stamp; };
 constexpr int kFwdRecords = 256;
 FwdRecord g_records[kFwdRecords];
 unsigned long g_record_clock = 0;
@@ -67,7 +68,7 @@ void record_forward(const void* ws, const Plan& pl) {
         if (g_records[e].ws == ws && g_records[e].dev == dev) { slot = e; break; }
         if (g_records[e].stamp < g_records[slot].stamp) slot = e;
     }
-    g_records[slot] = FwdRecord{ws, dev, pl.B, pl.N, pl.C, pl.K, pl.D, pl.R, pl.with_grad, pl.use_tc, pl.fused, ++g_record_clock};
+    g_records[slot] = FwdRecord{ws, dev, pl.B, pl.N, pl.C, pl.K, pl.D, pl.R, pl.with_grad, pl.use_tc, pl.fused, pl.c1, ++g_record_clock};
 }
 bool lookup_forward(const void* ws, FwdRecord& out) {
     int dev = 0;
@@ -79,7 +80,7 @@ bool lookup_forward(const void* ws, FwdRecord& out) {
 }
 
 // ---- launch accounting (bench.py: gpu_launches, per-kernel-class CUDA-event times) -------------
-enum KClass { kcLayout = 0, kcPassA0, kcPassL, kcPassA, kcSquash, kcSoftmax, kcGrad, kcReduceDu, kcLoss, kcOther, kcFused, kcCount };
+enum KClass { kcLayout = 0, kcPassA0, kcPassL, kcPassA, kcSquash, kcSoftmax, kcGrad, kcReduceDu, kcLoss, kcOther, kcFused, kcC1, kcCount };
 std::atomic<long> g_launches{0};
 int g_prof_on = 0;
 constexpr int kProfPool = 8192;
@@ -132,6 +133,7 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.tc_ok = p.DP >= 16 && C >= 2 && (p.DP != 16 || C >= 4);      // shape is eligible: sizes the layout
     p.use_tc = g_tune_tc != 0 && p.tc_ok;                          // engine choice: a knob
     p.fused = g_tune_fused != 0 && fused_supported(p);
+    p.c1 = g_tune_c1 != 0 && c1_supported(N, C, K, D);
     // split the i range until the grid fills the machine: the FMA kernel wants ~4 CTAs per SM, the tcgen05
     // kernel owns an SM (all of TMEM), so one wave of its CTAs (128-sample quads x 8-capsule groups) is enough
     const long ctas = p.use_tc ? (long)cdiv(C, tc_jw(p.DP)) * cdiv(p.nbt, 4) : (long)p.JG * p.ntg;
@@ -170,7 +172,8 @@ bool make_plan(Plan& p, int B, int N, int C, int K, int D, int R, int with_grad)
     p.o_beta = o; o += p.with_grad ? p.cs * (p.Reff > 1 ? p.Reff - 1 : 0) : 0;
     p.o_tmp = o; o += p.with_grad && p.Reff > 1 ? p.cs : 0;
     p.o_ds = o; o += p.with_grad ? p.xs * p.Reff : 0;
-    p.o_dupart = o; o += p.with_grad ? p.us * std::max(p.JG, cdiv(C * cdiv(p.DP, 16), 8)) : 0;   // FMA kernel: JG partials; mma kernel: <= cdiv(C * D/16, 8)
+    p.o_dupart = o; o += p.with_grad ? std::max(p.us * std::max(p.JG, cdiv(C * cdiv(p.DP, 16), 8)),
+                                                 c1_supported(N, C, K, D) ? round64(c1_part_floats(B, N, K, D)) : (size_t)0) : 0;   // FMA kernel: JG partials; mma kernel: <= cdiv(C * D/16, 8)
     p.total = o;
     return true;
 }
@@ -288,6 +291,7 @@ int caps_set_tuning(const char* name, int value) {
     if (!strcmp(name, "hostmb")) { g_tune_hostmb = value; return 0; }
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "fused")) { g_tune_fused = value != 0; return 0; }
+    if (!strcmp(name, "c1")) { g_tune_c1 = value != 0; return 0; }
     if (!strcmp(name, "isplit")) {
         if (value < 0 || value > kMaxSplits) return fail(CAPS_E_BADARG, "isplit must be in [0,%d]", kMaxSplits);
         g_tune_isplit = value;
@@ -320,6 +324,18 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
     float* ut = w + pl.o_ut;
     const float* Wp = W;
     int rc;
+    if (pl.c1) {
+        // one class capsule: softmax == 1, the layer is v = squash(u . W) whatever n_iter is -- one kernel, u read in place
+        { LaunchScope ls_(kcC1, st); rc = launch_c1_forward(u, W, v, w + pl.o_s, B, N, K, D, st); }
+        if (rc) return rc;
+        record_forward(ws, pl);
+        if (c_out != nullptr) {
+            const long n = (long)B * N * C;
+            { LaunchScope ls_(kcOther, st); k_fill<<<cdiv(n, 256), 256, 0, st>>>(c_out, 1.f, n); }
+            LAUNCH_CHECK();
+        }
+        return 0;
+    }
     if (pl.pad_w) {
         const long rows = (long)N * C * K;
         { LaunchScope ls_(kcLayout, st); k_pad_w<<<cdiv(rows * pl.DP, 256), 256, 0, st>>>(W, w + pl.o_wp, rows, D, pl.DP); }
@@ -396,7 +412,12 @@ int caps_route_forward(const float* u, const float* W, float* v, float* c_out, v
 int caps_route_backward(const float* u, const float* W, const float* grad_v, const int64_t* y, float margin_scale,
                         const float* loss_grad_dev, float* du, float* dW, void* ws, size_t ws_bytes,
                         int B, int N, int C, int K, int D, int R, void* stream) {
-    (void)u;
+    return caps_route_backward_ev(u, W, grad_v, y, margin_scale, loss_grad_dev, du, dW, ws, ws_bytes, B, N, C, K, D, R, stream, nullptr);
+}
+
+int caps_route_backward_ev(const float* u, const float* W, const float* grad_v, const int64_t* y, float margin_scale,
+                           const float* loss_grad_dev, float* du, float* dW, void* ws, size_t ws_bytes,
+                           int B, int N, int C, int K, int D, int R, void* stream, void* dw_ready_event) {
     Plan pl;
     if (!make_plan(pl, B, N, C, K, D, R, 1))
         return fail(CAPS_E_UNSUPPORTED, "caps_route_backward: dims B=%d N=%d C=%d K=%d D=%d R=%d not supported", B, N, C, K, D, R);
@@ -404,6 +425,7 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
     if (!W || !dW) return fail(CAPS_E_BADARG, "caps_route_backward: null pointer");
     if (B == 0) {
         CUDA_TRY(cudaMemsetAsync(dW, 0, (size_t)N * C * K * D * sizeof(float), st));
+        if (dw_ready_event) CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(dw_ready_event), st));
         return 0;
     }
     if (!ws) return fail(CAPS_E_BADARG, "caps_route_backward: null workspace");
@@ -423,6 +445,17 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         if (!rec.with_grad) return fail(CAPS_E_STATE, "caps_route_backward: the forward ran with with_grad = 0 (no saved state)");
         pl.use_tc = rec.use_tc;
         pl.fused = rec.fused;
+        pl.c1 = rec.c1;
+    }
+    if (pl.c1) {
+        if (!u) return fail(CAPS_E_BADARG, "caps_route_backward: u is required for a single class capsule");
+        float* w1 = static_cast<float*>(ws);
+        int nl = 0, rc1;
+        g_launches.fetch_add(1, std::memory_order_relaxed);       // two launches inside: count the second one here
+        { LaunchScope ls_(kcC1, st); rc1 = launch_c1_backward(u, W, w1 + pl.o_s, grad_v, y, margin_scale, loss_grad_dev, du, dW,
+                                                              w1 + pl.o_dupart, B, N, K, D, st, &nl); }
+        if (!rc1 && dw_ready_event) CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(dw_ready_event), st));
+        return rc1;
     }
     float* w = static_cast<float*>(ws);
     const float* ut = w + pl.o_ut;
@@ -499,6 +532,8 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
         rc = grad_mma ? launch_grad_mma(pl, gp, st) : launch_grad(pl, gp, st);
     }
     if (rc) return rc;
+    // dW is complete here (the du reduction below does not touch it): a data-parallel caller starts its all-reduce now
+    if (dw_ready_event) CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(dw_ready_event), st));
     if (du != nullptr) {
         const long n = (long)pl.nbt * N * 32;
         const int parts = grad_mma ? grad_mma_parts(pl) : pl.JG;
@@ -727,6 +762,110 @@ int caps_route_step_host(const float* u_host, const int64_t* y_host, const float
     if (du_host) CUDA_TRY(cudaMemcpyAsync(du_host, du_d, (size_t)B * N * K * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (L.nmb > 1) *loss_host = (loss_parts[0] + loss_parts[1]) + loss_parts[2];
+    return 0;
+}
+
+// ---- host pipeline: the H2D copy of step n+1 runs under the kernels of step n ---------------------------------
+namespace {
+struct HostPipe {
+    int B, N, C, K, D, R, dev;
+    char* base;
+    size_t o_u[2], o_y[2], o_v, o_loss, o_lscr, o_ws, ws_bytes, total;
+    cudaStream_t copy_stream;
+    cudaEvent_t copied[2];        // slot s: its H2D copies have landed
+    cudaEvent_t consumed[2];      // slot s: the step that read it has finished with u / y
+    long submitted, stepped;
+};
+bool host_pipe_layout(HostPipe& P) {
+    auto r256 = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    const size_t wsb = caps_route_workspace_bytes(P.B, P.N, P.C, P.K, P.D, P.R, 1);
+    if (wsb == 0 || P.B <= 0) return false;
+    size_t o = 0;
+    for (int s = 0; s < 2; ++s) { P.o_u[s] = o; o += r256((size_t)P.B * P.N * P.K * 4); P.o_y[s] = o; o += r256((size_t)P.B * 8); }
+    P.o_v = o; o += r256((size_t)P.B * P.C * P.D * 4);
+    P.o_loss = o; o += 256;
+    P.o_lscr = o; o += r256(CAPS_MARGIN_SCRATCH_FLOATS * 4);
+    P.o_ws = o; o += r256(wsb);
+    P.ws_bytes = wsb;
+    P.total = o;
+    return true;
+}
+}  // namespace
+
+size_t caps_host_pipe_scratch_bytes(int B, int N, int C, int K, int D, int R) {
+    HostPipe P{};
+    P.B = B; P.N = N; P.C = C; P.K = K; P.D = D; P.R = R;
+    return host_pipe_layout(P) ? P.total : 0;
+}
+
+int caps_host_pipe_create(void** pipe_out, void* dev_scratch, size_t scratch_bytes, int B, int N, int C, int K, int D, int R) {
+    if (!pipe_out || !dev_scratch) return fail(CAPS_E_BADARG, "caps_host_pipe_create: null pointer");
+    HostPipe* P = new HostPipe();
+    P->B = B; P->N = N; P->C = C; P->K = K; P->D = D; P->R = R;
+    if (!host_pipe_layout(*P)) { delete P; return fail(CAPS_E_UNSUPPORTED, "caps_host_pipe_create: dims not supported"); }
+    if (scratch_bytes < P->total) { const size_t need = P->total; delete P; return fail(CAPS_E_WORKSPACE, "caps_host_pipe_create: scratch %zu < %zu", scratch_bytes, need); }
+    P->base = static_cast<char*>(dev_scratch);
+    cudaError_t e = cudaGetDevice(&P->dev);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P->copy_stream, cudaStreamNonBlocking);
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+        e = cudaEventCreateWithFlags(&P->copied[s], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P->consumed[s], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { delete P; return fail((int)e, "caps_host_pipe_create: %s", cudaGetErrorString(e)); }
+    P->submitted = P->stepped = 0;
+    *pipe_out = P;
+    return 0;
+}
+
+int caps_host_pipe_destroy(void* pipe) {
+    HostPipe* P = static_cast<HostPipe*>(pipe);
+    if (!P) return 0;
+    cudaStreamSynchronize(P->copy_stream);
+    for (int s = 0; s < 2; ++s) { cudaEventDestroy(P->copied[s]); cudaEventDestroy(P->consumed[s]); }
+    cudaStreamDestroy(P->copy_stream);
+    delete P;
+    return 0;
+}
+
+int caps_host_pipe_submit(void* pipe, const float* u_host, const int64_t* y_host) {
+    HostPipe* P = static_cast<HostPipe*>(pipe);
+    if (!P || !u_host || !y_host) return fail(CAPS_E_BADARG, "caps_host_pipe_submit: null pointer");
+    if (P->submitted - P->stepped >= 2) return fail(CAPS_E_STATE, "caps_host_pipe_submit: both slots hold batches that have not been stepped");
+    const int s = (int)(P->submitted & 1);
+    // the slot's previous tenant (two submissions ago) must have been consumed by its step
+    if (P->submitted >= 2) CUDA_TRY(cudaStreamWaitEvent(P->copy_stream, P->consumed[s], 0));
+    CUDA_TRY(cudaMemcpyAsync(P->base + P->o_y[s], y_host, (size_t)P->B * 8, cudaMemcpyHostToDevice, P->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(P->base + P->o_u[s], u_host, (size_t)P->B * P->N * P->K * 4, cudaMemcpyHostToDevice, P->copy_stream));
+    CUDA_TRY(cudaEventRecord(P->copied[s], P->copy_stream));
+    ++P->submitted;
+    return 0;
+}
+
+int caps_host_pipe_step(void* pipe, const float* W_dev, float* dW_dev, float* loss_host, float* v_host, void* stream,
+                        void* dw_ready_event) {
+    HostPipe* P = static_cast<HostPipe*>(pipe);
+    if (!P || !W_dev || !dW_dev || !loss_host) return fail(CAPS_E_BADARG, "caps_host_pipe_step: null pointer");
+    if (P->stepped >= P->submitted) return fail(CAPS_E_STATE, "caps_host_pipe_step: no submitted batch to step on");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int s = (int)(P->stepped & 1);
+    const float* u_d = reinterpret_cast<const float*>(P->base + P->o_u[s]);
+    const int64_t* y_d = reinterpret_cast<const int64_t*>(P->base + P->o_y[s]);
+    float* v_d = reinterpret_cast<float*>(P->base + P->o_v);
+    float* loss_d = reinterpret_cast<float*>(P->base + P->o_loss);
+    void* ws = P->base + P->o_ws;
+    const int B = P->B, N = P->N, C = P->C, K = P->K, D = P->D, R = P->R;
+    int rc;
+    CUDA_TRY(cudaStreamWaitEvent(st, P->copied[s], 0));
+    if ((rc = caps_route_forward(u_d, W_dev, v_d, nullptr, ws, P->ws_bytes, B, N, C, K, D, R, 1, stream))) return rc;
+    if ((rc = caps_margin_loss(v_d, y_d, 1.f / (float)B, loss_d, nullptr, reinterpret_cast<float*>(P->base + P->o_lscr), B, C, D, stream))) return rc;
+    if ((rc = caps_route_backward_ev(u_d, W_dev, nullptr, y_d, 1.f / (float)B, nullptr, nullptr, dW_dev, ws, P->ws_bytes,
+                                     B, N, C, K, D, R, stream, dw_ready_event)))
+        return rc;
+    CUDA_TRY(cudaEventRecord(P->consumed[s], st));
+    CUDA_TRY(cudaMemcpyAsync(loss_host, loss_d, 4, cudaMemcpyDeviceToHost, st));
+    if (v_host) CUDA_TRY(cudaMemcpyAsync(v_host, v_d, (size_t)B * C * D * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ++P->stepped;
     return 0;
 }
 

@@ -46,7 +46,7 @@ constexpr int kMaxSplits = 32;     // splits of the i range any sweep may use (s
 struct Plan {
     int B, N, C, K, D, R, Reff, DP, JW, JG, SPT, nbt, ntg, IS, i_per_split, M;
     int CSmax;                         // capsules per coefficient row the layout reserves (C, or C rounded up to 8 where the fused sweep may run)
-    bool pad_w, with_grad, use_tc, tc_ok, fused;
+    bool pad_w, with_grad, use_tc, tc_ok, fused, c1;
     size_t xs, cs, us;                 // floats per X / coef / ut array
     // offsets (floats) into the workspace
     size_t o_ua, o_wb, o_ut, o_wp, o_vsum, o_s, o_v, o_part, o_c, o_beta, o_tmp, o_ds, o_dupart, total;
@@ -76,5 +76,12 @@ int fused_pick_splits(const Plan& pl, bool bwd, int forced);
 int launch_sweep_fused(const Plan& pl, bool bwd, const float* ua, const float* wb, const float* X, const float* coef_in,
                        const float* beta_in, float* coef_out, float* part, int IS, cudaStream_t st);
 int launch_coef_public(const Plan& pl, const float* coef, int CS, float* c_pub, cudaStream_t st);
+// caps_c1.cu: one class capsule (the DarkCapsuleNet head): the layer is one skinny GEMM + squash
+bool c1_supported(int N, int C, int K, int D);
+size_t c1_part_floats(int B, int N, int K, int D);
+int launch_c1_forward(const float* u, const float* W, float* v, float* s_save, int B, int N, int K, int D, cudaStream_t st);
+int launch_c1_backward(const float* u, const float* W, const float* s_save, const float* grad_v, const int64_t* y,
+                       float margin_scale, const float* loss_grad, float* du, float* dW, float* part,
+                       int B, int N, int K, int D, cudaStream_t st, int* launches);
 
 }  // namespace caps

@@ -39,7 +39,16 @@ def shard_bounds(n, rank, world):
 
 
 class GradBucket:
-    """Flat gradient bucket: p.grad of every parameter is a view into `self.flat`."""
+    """Flat gradient bucket: p.grad of every parameter is a view into `self.flat`, so the backward kernels' outputs
+    land in the buffer the collective reduces, and ONE all-reduce per step covers routing weights and backbone alike.
+
+    The all-reduce can run on a side stream behind an event (`allreduce_async(ready_event)`): the routing backward
+    records that event right behind the kernel that completes dW (caps_route_backward_ev), so the collective overlaps
+    the rest of the backward and the next step's forward; `wait()` makes the current stream wait for it (no host block).
+
+    `optimizer.zero_grad()` defaults to set_to_none=True since torch 2.0, which would silently detach the gradients
+    from the bucket: use `bucket.zero()` instead, or call zero_grad(set_to_none=False); `allreduce*` re-binds (and
+    copies) any gradient that no longer lives in the bucket, so a stale bucket is never reduced."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -48,13 +57,41 @@ class GradBucket:
         dev, dt = self.params[0].device, self.params[0].dtype
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, device=dev, dtype=dt)
+        self._views = []
         o = 0
         for p in self.params:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            view = self.flat[o:o + p.numel()].view_as(p)
+            p.grad = view
+            self._views.append(view)
             o += p.numel()
+        self._work = None
+        self._comm_stream = None
+        self._average_pending = False
 
     def zero(self):
         self.flat.zero_()
+
+    def rebind(self):
+        """Puts every .grad back into the bucket (copying what was accumulated elsewhere).  Returns how many had left."""
+        moved = 0
+        for p, view in zip(self.params, self._views):
+            g = p.grad
+            if g is None:
+                view.zero_()
+                p.grad = view
+                moved += 1
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
+                p.grad = view
+                moved += 1
+        return moved
+
+    def _reduce(self, average, async_op):
+        world = dist.get_world_size()
+        avg_native = average and self.flat.is_cuda            # NCCL has ReduceOp.AVG; gloo does not
+        op = dist.ReduceOp.AVG if avg_native else dist.ReduceOp.SUM
+        work = dist.all_reduce(self.flat, op=op, async_op=async_op)
+        return work, (average and not avg_native), world
 
     def allreduce(self, average=True, async_op=False):
         """Sum (or average) the bucket across ranks.  Each rank computes its loss with 1/B_local
@@ -62,9 +99,37 @@ class GradBucket:
         the concatenated batch when shards are equal."""
         if not dist.is_initialized() or dist.get_world_size() == 1:
             return None
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
-        if average:
+        self.rebind()
+        work, need_div, world = self._reduce(average, async_op)
+        if need_div:
             if async_op:
                 work.wait()
-            self.flat.div_(dist.get_world_size())
+            self.flat.div_(world)
         return work
+
+    def allreduce_async(self, ready_event=None, average=True):
+        """Enqueue the all-reduce on the bucket's side stream, behind `ready_event` (a torch.cuda.Event recorded when
+        the last gradient of the bucket is complete; None = behind everything queued on the current stream)."""
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return None
+        self.rebind()
+        if not self.flat.is_cuda:
+            return self.allreduce(average=average)
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.flat.device)
+        if ready_event is None:
+            ready_event = torch.cuda.Event()
+            ready_event.record()
+        self._comm_stream.wait_event(ready_event)
+        with torch.cuda.stream(self._comm_stream):
+            self._work, self._average_pending, _ = self._reduce(average, True)
+        return self._work
+
+    def wait(self):
+        """The current stream waits for the pending asynchronous all-reduce (stream-level: the host does not block)."""
+        if self._work is not None:
+            self._work.wait()
+            if self._average_pending:
+                self.flat.div_(dist.get_world_size())
+            self._work = None
+            self._average_pending = False

@@ -20,9 +20,16 @@
  *               c [B,N,C] (last-iteration coupling coefficients)   y [B] int64 labels
  *   - return value: 0 on success; CAPS_E_* (<0) for argument errors; a positive cudaError_t if a
  *     CUDA call failed.  caps_last_error() returns a thread-local message for the last failure.
- *   - the library keeps no global mutable state apart from the caps_set_tuning() knobs;
- *     launchers are re-entrant; the caller owns every
- *     buffer (inputs, outputs, workspace) for the duration of the enqueued work.
+ *   - the caller owns every buffer (inputs, outputs, workspace) for the duration of the enqueued work; launchers are
+ *     re-entrant across host threads and devices.  Process-wide state is limited to: the caps_set_tuning() knobs;
+ *     per-device caches of kernel attributes and one internal copy stream per device (created on first use, mutex-
+ *     guarded); a fixed-size, mutex-guarded table that remembers, per workspace pointer, the dims and engines of the
+ *     last caps_route_forward so that caps_route_backward can validate its workspace (CAPS_E_STATE) and replay them;
+ *     and the profiling counters of the measurement helpers (single-threaded use).
+ *   - results are bit-reproducible run to run for identical (dims, B, tuning, device model): every cross-CTA sum has
+ *     a fixed order, but how the input-capsule range is split across CTAs depends on the batch size and on how many
+ *     thread-block clusters the device can co-schedule, so the same sample can differ in its last bits between two
+ *     batch sizes (caps_set_tuning("isplit", n) pins the split).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef CAPS_ROUTING_H_
@@ -35,12 +42,12 @@
 extern "C" {
 #endif
 
-#define CAPS_ABI_VERSION 2
+#define CAPS_ABI_VERSION 3
 
 #define CAPS_E_BADARG     (-1)   /* null pointer / non-positive dim / misaligned pointer        */
 #define CAPS_E_UNSUPPORTED (-2)  /* K != 8, D > 48, R > 5, C > 1024: shapes with no kernel       */
 #define CAPS_E_WORKSPACE  (-3)   /* workspace smaller than caps_route_workspace_bytes() says     */
-#define CAPS_E_STATE      (-4)   /* backward called on a workspace that holds no forward state   */
+#define CAPS_E_STATE      (-4)   /* backward on a workspace no (matching, with_grad) forward filled; pipe misuse */
 
 /* ABI version of the loaded library (== CAPS_ABI_VERSION of the header it was built from). */
 int caps_abi_version(void);
@@ -78,6 +85,15 @@ int caps_route_backward(const float* u, const float* W, const float* grad_v, con
                         float margin_scale, const float* loss_grad_dev, float* du, float* dW,
                         void* ws, size_t ws_bytes,
                         int B, int N, int C, int K, int D, int R, void* stream);
+
+/* caps_route_backward plus a hook for data-parallel callers: `dw_ready_event` (a cudaEvent_t passed as void*, or
+ * NULL) is recorded on `stream` right behind the kernel that completes dW -- before the du reduction -- so that an
+ * all-reduce of dW on another stream can start while this stream finishes du (the reference has no
+ * counterpart: it is single-device, main.py:231). */
+int caps_route_backward_ev(const float* u, const float* W, const float* grad_v, const int64_t* y,
+                           float margin_scale, const float* loss_grad_dev, float* du, float* dW,
+                           void* ws, size_t ws_bytes,
+                           int B, int N, int C, int K, int D, int R, void* stream, void* dw_ready_event);
 
 /* Margin loss value: sum_{b,j} [ T relu(0.9-m)^2 + 0.5 (1-T) relu(m-0.1)^2 ] * scale with
  * m = |v[b,j,:]|, T = (y[b]==j).  Replaces reference models.py:117 + loss_fns.py:12-17,23
@@ -143,11 +159,28 @@ int caps_route_step_host(const float* u_host, const int64_t* y_host, const float
                          void* dev_scratch, size_t scratch_bytes,
                          int B, int N, int C, int K, int D, int R, void* stream);
 
+/* HOST pipeline: like caps_route_step_host, but the host->device copy of the NEXT step's inputs runs on an
+ * internal stream while the current step computes (two device input slots).  Replaces the per-batch
+ * `torch.from_numpy(x).to(device)` of the reference's train loop (main.py:57-59) on the routing-alone path.
+ *   scratch   caps_host_pipe_scratch_bytes(...) bytes of device memory, owned by the caller for the pipe's lifetime
+ *   submit    enqueues the H2D copy of one batch (u_host [B,N,K], y_host [B] int64; HOST, pinned for overlap) into
+ *             the free slot; at most two batches may be submitted and not yet stepped (CAPS_E_STATE otherwise)
+ *   step      waits for the oldest submitted batch, runs forward + margin loss + fused backward on `stream`
+ *             (du is not produced: no backbone below this entry point), copies the loss (and v if non-NULL) to the
+ *             host and synchronises `stream`.  dw_ready_event as in caps_route_backward_ev.
+ * Typical loop:  submit(b0); for n: { submit(b[n+1]); step(...); }   A pipe belongs to one host thread at a time. */
+size_t caps_host_pipe_scratch_bytes(int B, int N, int C, int K, int D, int R);
+int caps_host_pipe_create(void** pipe_out, void* dev_scratch, size_t scratch_bytes, int B, int N, int C, int K, int D, int R);
+int caps_host_pipe_submit(void* pipe, const float* u_host, const int64_t* y_host);
+int caps_host_pipe_step(void* pipe, const float* W_dev, float* dW_dev, float* loss_host, float* v_host, void* stream,
+                        void* dw_ready_event);
+int caps_host_pipe_destroy(void* pipe);
+
 /* Measurement helpers (bench.py).  caps_kernel_launch_count: kernels this library has launched in
  * this process.  With caps_set_tuning("profile", 1) every launch is bracketed by CUDA events on
  * its own stream; caps_profile_collect synchronises them, sums milliseconds / launch counts per
  * kernel class (0 layout, 1 pass-A0, 2 pass-L, 3 pass-A, 4 squash, 5 softmax, 6 grad, 7 du-reduce,
- * 8 loss, 9 other) and resets.  Profiling state is process-global: single-threaded use only.
+ * 8 loss, 9 other, 10 fused sweep, 11 single-capsule kernels) and resets.  Profiling state is process-global: single-threaded use only.
  * caps_fma_peak: times `iters` x 16 dependent-chain FFMAs per thread on a full grid and returns
  * milliseconds and the flop count (the fp32-FMA roofline denominator). */
 long caps_kernel_launch_count(void);
@@ -160,6 +193,10 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
  *   name = "tc"   1 (default): tcgen05 tensor-core pass kernel where it applies (9 <= D <= 16 and C >= 4, or
  *                 17 <= D <= 48 and C >= 2; D is zero-padded to 16 / 24 / 32 / 48);
  *                 0: fp32-FMA pass kernel everywhere
+ *   name = "fused" 1 (default): one cluster-fused sweep per routing iteration (logits -> softmax -> weighted sum, and
+ *                 its backward counterpart) where it applies (9 <= D <= 16, 4 <= C <= 64); 0: three kernels per iteration
+ *                 with max-subtracted softmax (the fused sweep exponentiates logits directly: |logit| must stay < 80)
+ *   name = "c1"   1 (default): dedicated GEMM + squash kernels for a single class capsule (C == 1, D <= 8); 0: general kernels
  *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
  *                 (D >= 9, C >= 7); 0: fp32-FMA gradient kernel everywhere

@@ -33,6 +33,18 @@ def _worker(rank, world, port, out):
     loss = ((x[lo:hi] @ W + b) ** 2).sum() / (hi - lo)       # per-rank 1/B_local like loss_fns.py:23
     loss.backward()
     bucket.allreduce(average=True)
+    first = bucket.flat.clone()
+    # a second step the way the reference's loop does it (main.py:70): optimizer.zero_grad() with set_to_none=True
+    # drops the views into the bucket; the bucket must notice, re-bind and still reduce the fresh gradients
+    torch.optim.SGD([W, b], lr=0.0).zero_grad()
+    assert W.grad is None
+    loss = ((x[lo:hi] @ W + b) ** 2).sum() / (hi - lo)
+    loss.backward()
+    assert W.grad.data_ptr() != bucket._views[0].data_ptr()
+    bucket.allreduce_async(None, average=True)               # CPU tensors: same result through the async entry point
+    bucket.wait()
+    assert W.grad.data_ptr() == bucket._views[0].data_ptr()
+    assert torch.allclose(bucket.flat, first, rtol=1e-6, atol=1e-6)
     if rank == 0:
         torch.save(bucket.flat.clone(), out)
     dist.destroy_process_group()

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_V = 1e-5
 TOL_G = 1e-4
-KNOB_DEFAULTS = {'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
+KNOB_DEFAULTS = {'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'c1': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
 
 
 @pytest.fixture(autouse=True)
@@ -309,6 +309,39 @@ def test_backward_validates_forward_state(capsb):
     _cabi.set_tuning('fused', 1)
     assert rel_err(dW.cpu().numpy(), ref['dW']) < 5e-6
     assert rel_err(du.cpu().numpy(), ref['du']) < 5e-6
+
+
+@pytest.mark.parametrize('dims', [
+    (1568, 512, 1, 8, 5, 3),      # the DarkCapsuleNet head at its real routing batch (32 images x 49 cells)
+    (7, 512, 1, 8, 5, 1),         # odd batch (the forward kernel takes samples in pairs), one iteration
+    (33, 24, 1, 8, 8, 2),         # D = 8, N*8 smaller than one pass of the thread block
+    (20, 100, 1, 8, 3, 3),
+])
+def test_single_capsule_head_kernels(capsb, dims):
+    """One class capsule (reference models.py:368-370): the dedicated GEMM + squash kernels (caps_c1.cu) against the
+    fp64 oracle and against the general kernels (tuning knob c1 = 0), with the fused margin gradient and an external
+    grad_v, as DarkCapsuleNet's loss feeds it (loss_fns.py:197)."""
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = dims
+    u, W, y = onp.make_inputs(B, N, C, K, D, seed=sum(dims))
+    gext = (np.random.default_rng(3).standard_normal((B, C, D)) * 0.05).astype(np.float32)
+    ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R, grad_v_extra=gext.astype(np.float64))
+    res = {}
+    for c1 in (1, 0):
+        capsb._cabi.set_tuning('c1', c1)
+        res[c1] = cuda_step(capsb, u, W, y, R, grad_v_extra=gext)
+        assert rel_err(res[c1]['v'], ref['v']) < TOL_V, c1
+        assert np.array_equal(res[c1]['c'], np.ones((B, N, 1), np.float32))
+        assert abs(res[c1]['loss'] - ref['loss']) < TOL_V * max(1.0, abs(ref['loss']))
+        assert rel_err(res[c1]['du'], ref['du']) < TOL_G, c1
+        assert rel_err(res[c1]['dW'], ref['dW']) < TOL_G, c1
+        assert_close_elementwise(res[c1]['dW'], ref['dW'], what='dW c1=%d' % c1)
+    for k in ('v', 'du', 'dW'):
+        assert rel_err(res[1][k], res[0][k]) < 5e-6, k
+    again = cuda_step(capsb, u, W, y, R, grad_v_extra=gext)          # c1 = 0 still set: fixed summation order either way
+    for k in ('v', 'du', 'dW'):
+        assert np.array_equal(again[k], res[0][k]), k
 
 
 def test_batch_permutation_and_additivity_at_full_size(capsb):

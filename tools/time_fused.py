@@ -12,7 +12,7 @@ from cs231_capsule_yolo_traffic_sign_detection_b200 import _cabi
 KCLASS = ['layout', 'pass_A0', 'pass_L', 'pass_A', 'squash', 'softmax', 'grad', 'du_reduce', 'loss', 'other', 'fused']
 L = _cabi.lib()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-N, C, K, D, R = 1152, 43, 8, 16, 3
+N, C, K, D, R = [int(x) for x in os.environ.get('CAPS_DIMS', '1152,43,8,16,3').split(',')]
 settings = sys.argv[2:] or ['fused=1']
 dev = torch.device('cuda')
 g = torch.Generator().manual_seed(0)
@@ -43,11 +43,12 @@ for setting in settings:
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
+    NREP = int(os.environ.get('CAPS_REPS', '3'))
+    for _ in range(NREP):
         step()
     e1.record()
     torch.cuda.synchronize()
-    total = e0.elapsed_time(e1) / 3
+    total = e0.elapsed_time(e1) / NREP
     _cabi.set_tuning('profile', 1)
     step()
     ms = (ctypes.c_double * len(KCLASS))(); n = (ctypes.c_long * len(KCLASS))()
