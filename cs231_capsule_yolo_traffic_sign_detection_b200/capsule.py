@@ -298,7 +298,11 @@ class CapsuleLayer(nn.Module):
     def __init__(self, params, n_caps, n_nodes, in_C, out_C, kernel=None, stride=None, n_iter=3):
         super(CapsuleLayer, self).__init__()
         self.params = params
-        self.n_iter = n_iter
+        # the reference hard-codes n_iter at its call sites (models.py:48, :93, :368); an optional `n_iter` entry in
+        # params.json (utils.Params attribute) overrides it for the routing branch -- the knob BASELINE.json's
+        # iteration sweep turns -- and is ignored when absent, so the reference's own params files behave as before
+        p_iter = getattr(params, 'n_iter', None) if n_nodes != -1 else None
+        self.n_iter = int(p_iter) if p_iter is not None else n_iter
         self.n_nodes = n_nodes
         self.n_caps = n_caps
         if n_nodes != -1:   # caps -> caps: the routing branch (models.py:56-58)

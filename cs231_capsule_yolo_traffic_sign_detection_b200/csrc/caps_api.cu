@@ -275,6 +275,7 @@ int caps_set_tuning(const char* name, int value) {
     }
     if (!strcmp(name, "tcdbg")) { g_tc_dbg = value; return 0; }
     if (!strcmp(name, "fsdbg")) { g_fs_dbg = value; return 0; }
+    if (!strcmp(name, "fsws")) { g_fs_ws = value != 0; return 0; }
     if (!strcmp(name, "fsinfo")) {          // prints what the fused sweep would do for C = value (diagnostics)
         fprintf(stderr, "[caps] fused sweep: cluster of %d CTAs, capacity fwd %d / bwd %d clusters\n", cdiv(value, 8),
                 fused_cluster_capacity(cdiv(value, 8), false), fused_cluster_capacity(cdiv(value, 8), true));
@@ -770,7 +771,7 @@ namespace {
 struct HostPipe {
     int B, N, C, K, D, R, dev;
     char* base;
-    size_t o_u[2], o_y[2], o_v, o_loss, o_lscr, o_ws, ws_bytes, total;
+    size_t o_u[2], o_y[2], o_v, o_du, o_loss, o_lscr, o_ws, ws_bytes, total;
     cudaStream_t copy_stream;
     cudaEvent_t copied[2];        // slot s: its H2D copies have landed
     cudaEvent_t consumed[2];      // slot s: the step that read it has finished with u / y
@@ -783,6 +784,7 @@ bool host_pipe_layout(HostPipe& P) {
     size_t o = 0;
     for (int s = 0; s < 2; ++s) { P.o_u[s] = o; o += r256((size_t)P.B * P.N * P.K * 4); P.o_y[s] = o; o += r256((size_t)P.B * 8); }
     P.o_v = o; o += r256((size_t)P.B * P.C * P.D * 4);
+    P.o_du = o; o += r256((size_t)P.B * P.N * P.K * 4);          // the step computes du like any backward (it stays on the device)
     P.o_loss = o; o += 256;
     P.o_lscr = o; o += r256(CAPS_MARGIN_SCRATCH_FLOATS * 4);
     P.o_ws = o; o += r256(wsb);
@@ -858,7 +860,7 @@ int caps_host_pipe_step(void* pipe, const float* W_dev, float* dW_dev, float* lo
     CUDA_TRY(cudaStreamWaitEvent(st, P->copied[s], 0));
     if ((rc = caps_route_forward(u_d, W_dev, v_d, nullptr, ws, P->ws_bytes, B, N, C, K, D, R, 1, stream))) return rc;
     if ((rc = caps_margin_loss(v_d, y_d, 1.f / (float)B, loss_d, nullptr, reinterpret_cast<float*>(P->base + P->o_lscr), B, C, D, stream))) return rc;
-    if ((rc = caps_route_backward_ev(u_d, W_dev, nullptr, y_d, 1.f / (float)B, nullptr, nullptr, dW_dev, ws, P->ws_bytes,
+    if ((rc = caps_route_backward_ev(u_d, W_dev, nullptr, y_d, 1.f / (float)B, nullptr, reinterpret_cast<float*>(P->base + P->o_du), dW_dev, ws, P->ws_bytes,
                                      B, N, C, K, D, R, stream, dw_ready_event)))
         return rc;
     CUDA_TRY(cudaEventRecord(P->consumed[s], st));

@@ -69,6 +69,7 @@ int launch_prep_w_tc(const Plan& pl, const float* W, float* wb, cudaStream_t st)
 int launch_pass_tc(const Plan& pl, int mode, const PassParams& pp, const float* ua, const float* wb, cudaStream_t st);
 // caps_sweep_fused.cu: one cluster-fused sweep per routing iteration (logits -> softmax -> weighted sum)
 extern int g_fs_dbg;                    // timing experiments only
+extern int g_fs_ws;                     // tuning knob "fsws": warp-specialised epilogue of the fused sweep (default 1)
 bool fused_supported(const Plan& pl);
 bool fused_shape_ok(int C, int DP, bool tc_ok);       // depends on the dims only (sizes the coefficient rows)
 int fused_cluster_capacity(int jg, bool bwd);

@@ -398,6 +398,301 @@ __global__ void __launch_bounds__(kFsThreads, 1) k_sweep_fused(FusedParams p) {
     cluster_sync_all();                      // no CTA leaves while a peer's stores may still be on their way to it
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised variant (tuning knob "fsws", default on): the same stages, barriers and exchange, but P1 and P2
+// are run by DIFFERENT warps -- 8 "logit" warps (P1) and 8 "accumulate" warps (P2) -- instead of one warp doing
+// P1(it) and then P2(it-2).  The epilogue is a chain of fixed latencies (barrier probe, tcgen05.ld, FFMA2 chain,
+// exchange, LDS) that two warps per scheduler cannot hide (ncu: 36 % issue utilisation); four warps per scheduler
+// with half the instruction stream each can.  The register state splits exactly: the probe vectors X live only in
+// the P1 warps, the accumulators only in the P2 warps (64 registers each), so 16 warps fit where 8 did.
+//   P1 -> P2 hand-over of e_j / dc_j: through the `ering` rows in shared memory as before; the receiver's wait on
+//   zfull[m] orders it (every P1 warp of every CTA arrived on its zlocal[m], a release, after storing its rows).
+//   P1 runs at most kFsAccum stages ahead of P2 (it needs accumulator it, which the issuer refills only after P2 of
+//   stage it-4 released it), so the ering holds kFsAccum slots and the credit-free argument for the 8-slot exchange
+//   ring still holds: a CTA sends row m only after its own P2(m-4), which needed every peer's row m-4, which each peer
+//   sent after its own P2(m-8).
+constexpr int kWsThreads = 640;            // warps 0-7 P1, 8-15 P2, 16 producer, 17 MMA issuer, 18 exchange, 19 idle
+constexpr int kWsEringSlots = kFsAccum;
+constexpr int kWsEringBytes = kWsEringSlots * kFsEpiWarps * 4 * 32 * 4;
+constexpr int kWsFixedBytes = kFsZpartBytes + kFsZrecvBytes + kWsEringBytes + kFsBarBytes;
+constexpr uint32_t kWsOffZpart = 0;
+constexpr uint32_t kWsOffZrecv = kWsOffZpart + kFsZpartBytes;
+constexpr uint32_t kWsOffEring = kWsOffZrecv + kFsZrecvBytes;
+constexpr uint32_t kWsOffBars = kWsOffEring + kWsEringBytes;
+constexpr uint32_t kWsOffSmemFull = kWsOffBars;
+constexpr uint32_t kWsOffSmemEmpty = kWsOffSmemFull + 8 * kFsMaxStages;
+constexpr uint32_t kWsOffTmemFull = kWsOffSmemEmpty + 8 * kFsMaxStages;
+constexpr uint32_t kWsOffTmemEmpty = kWsOffTmemFull + 8 * kFsAccum;
+constexpr uint32_t kWsOffZlocal = kWsOffTmemEmpty + 8 * kFsAccum;
+constexpr uint32_t kWsOffZfull = kWsOffZlocal + 8 * kFsZSlots;
+constexpr uint32_t kWsOffTmemSlot = kWsOffZfull + 8 * kFsZSlots;
+constexpr uint32_t kWsOffBaseSlot = kWsOffTmemSlot + 4;
+constexpr uint32_t kWsOffStages = (kWsFixedBytes + 1023) & ~1023u;
+static_assert(kWsOffBaseSlot + 4 <= kWsOffStages, "fixed region overflows");
+
+template <bool BWD>
+__global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t kStageBytes = fs_stage_bytes(BWD);
+    const int ns = p.ns;
+    const uint32_t base0 = smem_u32(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jg = blockIdx.x, tq = blockIdx.z;
+    const int i_begin = blockIdx.y * p.i_per_split;
+    const int i_end = min(p.N, i_begin + p.i_per_split);
+    const int n_i = max(i_end - i_begin, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ns; ++s) { mbar_init(base0 + kWsOffSmemFull + 8 * s, 1); mbar_init(base0 + kWsOffSmemEmpty + 8 * s, BWD ? kFsEpiWarps + 1 : 1); }
+        for (int t = 0; t < kFsAccum; ++t) { mbar_init(base0 + kWsOffTmemFull + 8 * t, 1); mbar_init(base0 + kWsOffTmemEmpty + 8 * t, kFsEpiWarps); }
+        for (int z = 0; z < kFsZSlots; ++z) { mbar_init(base0 + kWsOffZlocal + 8 * z, kFsEpiWarps); mbar_init(base0 + kWsOffZfull + 8 * z, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base0 + kWsOffBaseSlot), "r"(base0) : "memory");
+    }
+    for (int e = threadIdx.x; e < kFsZrecvBytes / 4; e += kWsThreads) sts_f32(base0 + kWsOffZrecv + 4 * e, 0.f);   // absent ranks add 0
+    if (warp == 17) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base0 + kWsOffTmemSlot), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t base, tmem_base;            // read back through shared memory: see k_sweep_fused
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(base) : "r"(base0 + kWsOffBaseSlot) : "memory");
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(base0 + kWsOffTmemSlot) : "memory");
+    cluster_sync_all();
+
+    if (warp >= 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        const uint32_t stages = base + kWsOffStages;
+        if (warp == 16) {
+            // ===== producer =====
+            const float* asrc = p.ua + ((size_t)tq * p.N + i_begin) * 2048;
+            const float* bsrc = p.wb + ((size_t)i_begin * p.JG + jg) * 2048;
+            const size_t bstep = (size_t)p.JG * 2048;
+            const size_t CS = (size_t)p.JG * 8;
+            const uint32_t cbytes = 8u * 128u;
+            const size_t ctile = (size_t)p.N * CS * kLanes;
+            const size_t coff = ((size_t)(tq * 4) * p.N + i_begin) * CS * kLanes + (size_t)jg * 8 * kLanes;
+            const float* csrc = BWD ? p.coef_in + coff : nullptr;
+            const float* esrc = (BWD && p.beta_in != nullptr) ? p.beta_in + coff : nullptr;
+            const size_t cstep = CS * kLanes;
+            const int nvt = min(4, p.nbt - tq * 4);
+            const uint32_t txbytes = (uint32_t)kFsOperandBytes + (BWD ? (uint32_t)nvt * cbytes * (esrc ? 2u : 1u) : 0u);
+            int s = 0;
+            uint32_t ph = 1;
+            for (int n = 0; n < n_i; ++n) {
+                mbar_wait_i(base + kWsOffSmemEmpty + 8 * s, ph);
+                if (elect_one()) {
+                    const uint32_t dst = stages + (uint32_t)s * kStageBytes, bar = base + kWsOffSmemFull + 8 * s;
+                    mbar_expect_tx(bar, txbytes);
+                    bulk_g2s(dst, asrc, 8192, bar);
+                    bulk_g2s(dst + 8192, bsrc, 8192, bar);
+                    if (BWD) {
+                        for (int tt = 0; tt < nvt; ++tt) {
+                            bulk_g2s(dst + kFsOperandBytes + tt * 1024, csrc + tt * ctile, cbytes, bar);
+                            if (esrc) bulk_g2s(dst + kFsOperandBytes + kFsCoefBytes + tt * 1024, esrc + tt * ctile, cbytes, bar);
+                        }
+                    }
+                }
+                __syncwarp();
+                asrc += 2048;
+                bsrc += bstep;
+                if (BWD) { csrc += cstep; if (esrc) esrc += cstep; }
+                if (++s == ns) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 17) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t desc0 = umma_desc(stages, 2048, 128);
+            int s = 0;
+            uint32_t sph = 0;
+            for (int n = 0; n < n_i; ++n) {
+                const int t = n & (kFsAccum - 1);
+                mbar_wait_i(base + kWsOffTmemEmpty + 8 * t, ((n >> 2) & 1) ^ 1);
+                mbar_wait_i(base + kWsOffSmemFull + 8 * s, sph);
+                tc_fence_after();
+                const uint64_t a_hi = desc0 + (uint64_t)((s * kStageBytes) >> 4);
+                const uint64_t a_lo = a_hi + (4096 >> 4), b_hi = a_hi + (8192 >> 4), b_lo = b_hi + (4096 >> 4);
+                umma_stage(tmem_base + (uint32_t)(t * 128), a_hi, a_lo, b_hi, b_lo, idesc, base + kWsOffSmemEmpty + 8 * s, base + kWsOffTmemFull + 8 * t);
+                if (++s == ns) { s = 0; sph ^= 1; }
+            }
+        } else if (warp == 18) {
+            // ===== exchange =====
+            const uint32_t nrank = (uint32_t)p.JG;
+            const uint32_t my_row = base + kWsOffZrecv + (uint32_t)jg * 512 + (uint32_t)lane * 16;
+            uint32_t raddr[kFsMaxCluster], rbar[kFsMaxCluster];
+#pragma unroll
+            for (int r = 0; r < kFsMaxCluster; ++r) {
+                const uint32_t rr = (uint32_t)r < nrank ? (uint32_t)r : 0u;
+                raddr[r] = mapa_u32(my_row, rr);
+                rbar[r] = mapa_u32(base + kWsOffZfull, rr);
+            }
+            for (int n = 0; n < n_i; ++n) {
+                const uint32_t slot = (uint32_t)n & (kFsZSlots - 1), par = ((uint32_t)n >> 3) & 1;
+                mbar_wait_i(base + kWsOffZlocal + 8 * slot, par);
+                const float4 a = lds_v4(base + kWsOffZpart + slot * 1024 + (uint32_t)lane * 16);
+                const float4 b = lds_v4(base + kWsOffZpart + slot * 1024 + 512 + (uint32_t)lane * 16);
+                const float4 z = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+                if (lane == 0) mbar_expect_tx(base + kWsOffZfull + 8 * slot, nrank * 512u);
+#pragma unroll
+                for (int r = 0; r < kFsMaxCluster; ++r)
+                    if ((uint32_t)r < nrank) st_async_v4(raddr[r] + slot * 4096, z, rbar[r] + 8 * slot);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // warp w (mod 8) -> samples of lane tile 4 tq + (w & 3), capsules jg*8 + 4 ((w >> 2) & 1) .. + 3
+        const int q = warp & 3, jh = (warp >> 2) & 1;
+        const int tile = tq * 4 + q;
+        const bool tvalid = tile < p.nbt;
+        const int j0 = jg * 8 + jh * 4;
+        const uint32_t tb = base + (uint32_t)(q * 32 + lane) * 4;
+        const uint32_t er_base = tb + kWsOffEring + (uint32_t)jh * 2048;                 // + (stage & 3) * 4096 + jj * 512
+        const uint32_t co_base = base + kWsOffStages + kFsOperandBytes + (uint32_t)((q * 8 + jh * 4) * kLanes + lane) * 4;   // + stage * kStageBytes + jj * 128
+        uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jh * 64);
+        asm volatile("mov.b32 %0, %0;" : "+r"(lane_base));
+        const uint32_t st_end = (uint32_t)ns * kStageBytes;
+        if (warp < kFsEpiWarps) {
+            // ===================== P1 warps: logits / dc, partial normaliser =====================
+            float lim[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                lim[jj] = (j0 + jj < p.C) ? 120.f : -200.f;
+                asm volatile("mov.b32 %0, %0;" : "+f"(lim[jj]));
+            }
+            float X[4][16];                 // FWD: log2(e) * sum of v; BWD: ds
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int d = 0; d < 16; ++d) X[jj][d] = 0.f;
+            if (tvalid) {
+                const float sc = BWD ? 1.f : 1.4426950408889634f;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    if (j0 + jj < p.C) {
+#pragma unroll
+                        for (int dq = 0; dq < 4; ++dq) {
+                            const float4 x = ldg4(p.X + ((((size_t)tile * p.C + j0 + jj) * 4 + dq) * kLanes + lane) * 4);
+                            X[jj][dq * 4 + 0] = x.x * sc; X[jj][dq * 4 + 1] = x.y * sc; X[jj][dq * 4 + 2] = x.z * sc; X[jj][dq * 4 + 3] = x.w * sc;
+                        }
+                    }
+            }
+            const uint32_t zp_base = tb + kWsOffZpart + (uint32_t)jh * 512;              // + zs * 1024
+            uint32_t st1 = 0;
+            for (int it = 0; it < n_i; ++it) {
+                const uint32_t t = (uint32_t)it & (kFsAccum - 1), zs = (uint32_t)it & (kFsZSlots - 1);
+                mbar_wait_i(base + kWsOffTmemFull + 8 * t, ((uint32_t)it >> 2) & 1);
+                tc_fence_after();
+                float z = 0.f;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float uh[16];
+                    tmem_ld16(lane_base + t * 128 + jj * 16, uh);
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 16; d += 4) {
+                        ffma2(d0, d1, uh[d], uh[d + 1], X[jj][d], X[jj][d + 1]);
+                        ffma2(d2, d3, uh[d + 2], uh[d + 3], X[jj][d + 2], X[jj][d + 3]);
+                    }
+                    const float dot = (d0 + d1) + (d2 + d3);
+                    float keep;
+                    if (!BWD) {
+                        keep = ex2_approx(fminf(dot, lim[jj]));
+                        z += keep;
+                    } else {
+                        keep = dot;
+                        z = fmaf(lds_f32(co_base + st1 + jj * 128), dot, z);
+                    }
+                    sts_f32(er_base + t * 4096 + jj * 512, keep);
+                }
+                sts_f32(zp_base + zs * 1024, z);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(base + kWsOffZlocal + 8 * zs);
+                if (BWD) { st1 += kStageBytes; if (st1 == st_end) st1 = 0; }
+            }
+        } else {
+            // ===================== P2 warps: normalise, store, accumulate =====================
+            const bool has_beta = BWD && p.beta_in != nullptr;
+            const bool do_store = tvalid && p.coef_out != nullptr && !(p.dbg & 2);             // warp-uniform
+            float acc[4][16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int d = 0; d < 16; ++d) acc[jj][d] = 0.f;
+            const uint32_t zr_base = tb + kWsOffZrecv;                                   // + zs * 4096 + rank * 512
+            uintptr_t cptr = reinterpret_cast<uintptr_t>(p.coef_out) + ((((size_t)(tvalid ? tile : 0) * p.N + i_begin) * (p.JG * 8) + j0) * kLanes + lane) * 4;
+            const uintptr_t cstep = (uintptr_t)p.JG * 8 * kLanes * 4;
+            uint32_t st2 = 0, sb2 = 0;
+            for (int m = 0; m < n_i; ++m) {
+                const uint32_t t = (uint32_t)m & (kFsAccum - 1), zs = (uint32_t)m & (kFsZSlots - 1);
+                mbar_wait_i(base + kWsOffZfull + 8 * zs, ((uint32_t)m >> 3) & 1);
+                const uint32_t zr = zr_base + zs * 4096;
+                float zz[kFsMaxCluster];
+#pragma unroll
+                for (int r = 0; r < kFsMaxCluster; ++r) zz[r] = lds_f32(zr + r * 512);
+                const float Z = ((zz[0] + zz[1]) + (zz[2] + zz[3])) + ((zz[4] + zz[5]) + (zz[6] + zz[7]));    // fixed order: same bits in every CTA
+                float f[4];
+                const float rz = BWD ? 0.f : rcp_approx(Z);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float keep = lds_f32(er_base + t * 4096 + jj * 512);
+                    if (!BWD) {
+                        f[jj] = keep * rz;
+                    } else {
+                        const float c = lds_f32(co_base + st2 + jj * 128);
+                        const float bp = has_beta ? lds_f32(co_base + st2 + kFsCoefBytes + jj * 128) : 0.f;
+                        f[jj] = fmaf(c, keep - Z, bp);
+                    }
+                }
+                if (do_store) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) reinterpret_cast<float*>(cptr)[jj * kLanes] = f[jj];
+                }
+                // the accumulator of stage m: its commit was observed by the P1 warps before they arrived on zlocal[m];
+                // taken again here (already complete) so that this warp's tcgen05.ld is ordered after it by itself
+                mbar_wait_i(base + kWsOffTmemFull + 8 * t, ((uint32_t)m >> 2) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float uh[16];
+                    tmem_ld16(lane_base + t * 128 + jj * 16, uh);
+                    if (jj == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(base + kWsOffTmemEmpty + 8 * t);               // accumulator t may be overwritten
+                            if (BWD) mbar_arrive(base + kWsOffSmemEmpty + sb2);        // and the coefficient rows of this stage
+                        }
+                    }
+#pragma unroll
+                    for (int d = 0; d < 16; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], uh[d], uh[d + 1]);
+                }
+                cptr += cstep;
+                if (BWD) { st2 += kStageBytes; sb2 += 8; if (st2 == st_end) { st2 = 0; sb2 = 0; } }
+            }
+            if (tvalid) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    if (j0 + jj < p.C) {
+#pragma unroll
+                        for (int dq = 0; dq < 4; ++dq)
+                            st4(p.part + (((((size_t)blockIdx.y * p.nbt + tile) * p.C + j0 + jj) * 4 + dq) * kLanes + lane) * 4,
+                                make_float4(acc[jj][dq * 4 + 0], acc[jj][dq * 4 + 1], acc[jj][dq * 4 + 2], acc[jj][dq * 4 + 3]));
+                    }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+    cluster_sync_all();
+}
+
 // couplings in the lane-tile layout [nbt][N][C][32] -> public [B][N][C] (tests and callers that ask for c_out)
 __global__ void k_coef_public(const float* __restrict__ coef, float* __restrict__ c_pub, int B, int N, int C, int CS, int nbt) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,16 +708,32 @@ __global__ void k_coef_public(const float* __restrict__ coef, float* __restrict_
 }
 
 struct ClusterCap { std::atomic<int> n[kMaxDevices][kFsMaxCluster + 1]; };      // 0 = not queried yet
-ClusterCap g_cap[2];
+ClusterCap g_cap[2][2];                                                          // [variant][bwd]
 
-template <bool BWD>
-int launch_t(const Plan& pl, const FusedParams& fp, int IS, cudaStream_t st) {
-    auto kern = k_sweep_fused<BWD>;
-    const size_t smem = (size_t)kOffStages + (size_t)fp.ns * fs_stage_bytes(BWD);
-    CAPS_SET_SMEM(kern, smem);
+inline size_t fs_fixed_bytes(bool ws) { return ws ? (size_t)kWsOffStages : (size_t)kOffStages; }
+
+int fs_stages(bool bwd, bool ws) {
+    int ns = bwd ? 7 : 8;
+    while (fs_fixed_bytes(ws) + (size_t)ns * fs_stage_bytes(bwd) > 227 * 1024) --ns;
+    return ns;
+}
+
+const void* fs_kernel(bool bwd, bool ws) {
+    if (ws) return bwd ? reinterpret_cast<const void*>(k_sweep_fused_ws<true>) : reinterpret_cast<const void*>(k_sweep_fused_ws<false>);
+    return bwd ? reinterpret_cast<const void*>(k_sweep_fused<true>) : reinterpret_cast<const void*>(k_sweep_fused<false>);
+}
+
+int launch_k(const Plan& pl, const FusedParams& fp, int IS, bool bwd, bool ws, cudaStream_t st) {
+    const void* kern = fs_kernel(bwd, ws);
+    const size_t smem = fs_fixed_bytes(ws) + (size_t)fp.ns * fs_stage_bytes(bwd);
+    {
+        static SmemAttrCache cache[2][2];
+        const int rc = ensure_dyn_smem(kern, smem, cache[ws ? 1 : 0][bwd ? 1 : 0]);
+        if (rc) return rc;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(fp.JG, IS, cdiv(pl.nbt, 4));
-    cfg.blockDim = dim3(kFsThreads);
+    cfg.blockDim = dim3(ws ? kWsThreads : kFsThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -430,19 +741,16 @@ int launch_t(const Plan& pl, const FusedParams& fp, int IS, cudaStream_t st) {
     attr[0].val.clusterDim.x = fp.JG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, fp));
+    FusedParams arg = fp;
+    void* args[1] = {&arg};
+    CUDA_TRY(cudaLaunchKernelExC(&cfg, kern, args));
     return 0;
-}
-
-int fs_stages(bool bwd) {
-    int ns = bwd ? 7 : 8;
-    while ((size_t)kOffStages + (size_t)ns * fs_stage_bytes(bwd) > 227 * 1024) --ns;
-    return ns;
 }
 
 }  // namespace
 
 int g_fs_dbg = 0;
+int g_fs_ws = 1;         // tuning knob "fsws": 1 = warp-specialised epilogue (8 logit warps + 8 accumulate warps), 0 = 8 warps doing both
 
 // D == 16 (after padding), 8 capsules per CTA, one cluster of ceil(C/8) <= 8 CTAs per (128 samples, i range)
 bool fused_shape_ok(int C, int DP, bool tc_ok) { return tc_ok && DP == 16 && cdiv(C, 8) <= kFsMaxCluster; }
@@ -450,17 +758,18 @@ bool fused_supported(const Plan& pl) { return pl.use_tc && pl.Reff > 1 && fused_
 
 // clusters of `jg` CTAs the device can run at once (GPC granularity: not simply SMs / jg)
 int fused_cluster_capacity(int jg, bool bwd) {
+    const bool ws = g_fs_ws != 0;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || jg < 1 || jg > kFsMaxCluster) return 0;
-    std::atomic<int>& slot = g_cap[bwd ? 1 : 0].n[dev][jg];
+    std::atomic<int>& slot = g_cap[ws ? 1 : 0][bwd ? 1 : 0].n[dev][jg];
     int n = slot.load(std::memory_order_relaxed);
     if (n > 0) return n;
-    const size_t smem = (size_t)kOffStages + (size_t)fs_stages(bwd) * fs_stage_bytes(bwd);
-    const void* kern = bwd ? reinterpret_cast<const void*>(k_sweep_fused<true>) : reinterpret_cast<const void*>(k_sweep_fused<false>);
+    const size_t smem = fs_fixed_bytes(ws) + (size_t)fs_stages(bwd, ws) * fs_stage_bytes(bwd);
+    const void* kern = fs_kernel(bwd, ws);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(jg, 64, 1);
-    cfg.blockDim = dim3(kFsThreads);
+    cfg.blockDim = dim3(ws ? kWsThreads : kFsThreads);
     cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -468,8 +777,7 @@ int fused_cluster_capacity(int jg, bool bwd) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int nc = 0;
-    cudaError_t e = bwd ? cudaOccupancyMaxActiveClusters(&nc, k_sweep_fused<true>, &cfg)
-                        : cudaOccupancyMaxActiveClusters(&nc, k_sweep_fused<false>, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
     if (e != cudaSuccess || nc <= 0) { cudaGetLastError(); return 0; }
     slot.store(nc, std::memory_order_relaxed);
     return nc;
@@ -501,10 +809,11 @@ int launch_sweep_fused(const Plan& pl, bool bwd, const float* ua, const float* w
     fp.ua = ua; fp.wb = wb; fp.X = X; fp.coef_in = coef_in; fp.beta_in = beta_in; fp.coef_out = coef_out; fp.part = part;
     fp.N = pl.N; fp.C = pl.C; fp.JG = cdiv(pl.C, 8); fp.nbt = pl.nbt;
     fp.i_per_split = cdiv(cdiv(pl.N, IS), 4) * 4;
-    fp.ns = fs_stages(bwd);
+    const bool ws = g_fs_ws != 0;
+    fp.ns = fs_stages(bwd, ws);
     fp.dbg = g_fs_dbg;
     if (cdiv(pl.N, fp.i_per_split) != IS) return fail(CAPS_E_BADARG, "fused sweep: %d splits do not tile N=%d", IS, pl.N);
-    return bwd ? launch_t<true>(pl, fp, IS, st) : launch_t<false>(pl, fp, IS, st);
+    return launch_k(pl, fp, IS, bwd, ws, st);
 }
 
 int launch_coef_public(const Plan& pl, const float* coef, int CS, float* c_pub, cudaStream_t st) {

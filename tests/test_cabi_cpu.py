@@ -89,6 +89,11 @@ def test_module_mirrors_reference_interface(capsb):
     assert tuple(layer.route_weights.shape) == (1, 12, 43, 8, 16)
     torch.manual_seed(7)                               # reference models.py:57-58: 0.1 * randn(1,N,C,K,D)
     assert torch.equal(layer.route_weights.detach(), 0.1 * torch.randn(1, 12, 43, 8, 16))
+    # optional params.n_iter (the iteration-sweep knob); absent -> the constructor argument rules
+    class WithIter:
+        n_iter = 5
+    assert capsb.CapsuleLayer(WithIter(), n_caps=3, n_nodes=4, in_C=8, out_C=16).n_iter == 5
+    assert capsb.CapsuleLayer(object(), n_caps=3, n_nodes=4, in_C=8, out_C=16, n_iter=2).n_iter == 2
     prim = capsb.CapsuleLayer(None, n_caps=8, n_nodes=-1, in_C=16, out_C=4, kernel=3, stride=2)
     assert sorted(prim.state_dict().keys()) == sorted(
         ['capsules.%d.%s' % (i, w) for i in range(8) for w in ('weight', 'bias')])
