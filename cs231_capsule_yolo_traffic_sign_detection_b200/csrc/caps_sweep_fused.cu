@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
     cluster_sync_all();
 
     if (warp >= 16) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");      // 640 x 96 registers = 256 x 104 (P1) + 256 x 112 (P2) + 128 x 48
         const uint32_t stages = base + kWsOffStages;
         if (warp == 16) {
             // ===== producer =====
@@ -541,7 +541,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // warp w (mod 8) -> samples of lane tile 4 tq + (w & 3), capsules jg*8 + 4 ((w >> 2) & 1) .. + 3
         const int q = warp & 3, jh = (warp >> 2) & 1;
         const int tile = tq * 4 + q;
@@ -555,6 +554,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
         const uint32_t st_end = (uint32_t)ns * kStageBytes;
         if (warp < kFsEpiWarps) {
             // ===================== P1 warps: logits / dc, partial normaliser =====================
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
             float lim[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
             }
         } else {
             // ===================== P2 warps: normalise, store, accumulate =====================
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
             const bool has_beta = BWD && p.beta_in != nullptr;
             const bool do_store = tvalid && p.coef_out != nullptr && !(p.dbg & 2);             // warp-uniform
             float acc[4][16];
@@ -626,7 +627,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
             uint32_t st2 = 0, sb2 = 0;
             for (int m = 0; m < n_i; ++m) {
                 const uint32_t t = (uint32_t)m & (kFsAccum - 1), zs = (uint32_t)m & (kFsZSlots - 1);
+                // zfull[m] complete: every CTA's P1 warps are done with stage m (their rows are here), and each of them had
+                // observed the accumulator's commit before it arrived -- the chain zlocal -> exchange -> zfull orders this
+                // warp's tcgen05.ld behind that commit, so the accumulator barrier is not taken a second time
                 mbar_wait_i(base + kWsOffZfull + 8 * zs, ((uint32_t)m >> 3) & 1);
+                tc_fence_after();
+                uint32_t ur[16];
+                tmem_ld16_issue(lane_base + t * 128, ur);          // capsule 0's u_hat travels while Z is summed
                 const uint32_t zr = zr_base + zs * 4096;
                 float zz[kFsMaxCluster];
 #pragma unroll
@@ -649,14 +656,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) reinterpret_cast<float*>(cptr)[jj * kLanes] = f[jj];
                 }
-                // the accumulator of stage m: its commit was observed by the P1 warps before they arrived on zlocal[m];
-                // taken again here (already complete) so that this warp's tcgen05.ld is ordered after it by itself
-                mbar_wait_i(base + kWsOffTmemFull + 8 * t, ((uint32_t)m >> 2) & 1);
-                tc_fence_after();
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    float uh[16];
-                    tmem_ld16(lane_base + t * 128 + jj * 16, uh);
+                    if (jj > 0) tmem_ld16_issue(lane_base + t * 128 + jj * 16, ur);
+                    tmem_ld16_wait(ur);
                     if (jj == 3) {
                         tc_fence_before();
                         __syncwarp();
@@ -666,7 +669,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
                         }
                     }
 #pragma unroll
-                    for (int d = 0; d < 16; d += 2) ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], uh[d], uh[d + 1]);
+                    for (int d = 0; d < 16; d += 2)
+                        ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], __uint_as_float(ur[d]), __uint_as_float(ur[d + 1]));
                 }
                 cptr += cstep;
                 if (BWD) { st2 += kStageBytes; sb2 += 8; if (st2 == st_end) { st2 = 0; sb2 = 0; } }
