@@ -232,12 +232,16 @@ def main_gpu(args, rank, world, device):
     stream = torch.cuda.current_stream().cuda_stream
     P = lambda t: t.data_ptr()
 
-    def step_device():
+    def step_local():
+        # one rank's share of a step: forward, margin loss, backward (no collective: also what the parity check runs)
         _cabi.check(L.caps_route_forward(P(u), P(W), P(v), None, P(ws), nbytes, B, N, C, K, D, R, 1, stream), 'fwd')
         _cabi.check(L.caps_margin_loss(P(v), P(y), 1.0 / B, P(loss), None, P(lscr), B, C, D, stream), 'loss')
         bucket.wait()                      # the previous step's all-reduce must be done before dW is rewritten (stream-level)
         _cabi.check(L.caps_route_backward_ev(P(u), P(W), None, P(y), 1.0 / B, None, P(du), P(dW), P(ws), nbytes,
                                              B, N, C, K, D, R, stream, dw_ready.cuda_event), 'bwd')
+
+    def step_device():
+        step_local()
         if world > 1:
             # gradient AVERAGE across ranks on the bucket's comm stream, gated by the event the backward records right
             # behind the kernel that completes dW: overlaps the du reduction and the next step's forward
@@ -307,6 +311,7 @@ def main_gpu(args, rank, world, device):
     ms_e2e, _, _ = timed(step_host, args.steps)
     e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
 
+    barrier()                              # every collective of this run is complete on every rank
     if rank != 0:
         return 0
 
@@ -316,7 +321,7 @@ def main_gpu(args, rank, world, device):
     try:
         import numpy as np
         from oracle import routing_c as oc
-        step_device()
+        step_local()                       # rank 0 only from here on: nothing below may enter a collective
         torch.cuda.synchronize()
         ns = min(64, B)
         ref = oc.routing_step(u_host[:ns].numpy().astype(np.float64), W.cpu().numpy().astype(np.float64),

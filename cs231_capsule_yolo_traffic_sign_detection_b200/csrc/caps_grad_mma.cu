@@ -28,6 +28,7 @@ namespace caps {
 namespace {
 
 constexpr int kGmIT = 8;          // input capsules per CTA
+constexpr bool g_use_ffma2 = true;   // G build as 8 packed FMAs per term (scalar-broadcast coefficient) instead of 16 FFMA
 // Consumer warps (= output capsules) per CTA: 8 or 11.  11 + the producer warp = 384 threads is the most that still
 // leaves 168 registers per thread (X^m alone takes 16 M); three warps per scheduler instead of two hide more of the
 // LDS -> split -> HMMA chain, and C = 43 is 4 x 11 - 1.
@@ -315,8 +316,13 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
 #pragma unroll
                     for (int m = 1; m < M; ++m) {
                         const float al = crow[(m - 1) * JW * 32];
+                        if (g_use_ffma2) {
 #pragma unroll
-                        for (int d = 0; d < 16; ++d) G[d] = fmaf(al, xr[m][d], G[d]);
+                            for (int d = 0; d < 16; d += 2) ffma2(G[d], G[d + 1], al, al, xr[m][d], xr[m][d + 1]);
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < 16; ++d) G[d] = fmaf(al, xr[m][d], G[d]);
+                        }
                     }
                     __syncwarp();                                   // previous unit's fragment reads are done
 #pragma unroll

@@ -296,7 +296,8 @@ __global__ void k_squash(const float* __restrict__ part, int IS, size_t xsize, f
     float s[DP], v[DP];
 #pragma unroll
     for (int d = 0; d < DP; ++d) s[d] = 0.f;
-    for (int is = 0; is < IS; ++is)
+#pragma unroll 4
+    for (int is = 0; is < IS; ++is)   // unrolled: the partial loads of four splits are in flight together (same order of additions)
 #pragma unroll
         for (int dq = 0; dq < D4; ++dq) {
             const float4 x = ldg4(part + is * xsize + base + (size_t)dq * kLanes * 4);
@@ -356,6 +357,7 @@ __global__ void k_dsquash(const float* __restrict__ part, int IS, size_t xsize,
         s[dq * 4 + 0] = x.x; s[dq * 4 + 1] = x.y; s[dq * 4 + 2] = x.z; s[dq * 4 + 3] = x.w;
     }
     if (part != nullptr) {
+#pragma unroll 4
         for (int is = 0; is < IS; ++is)
 #pragma unroll
             for (int dq = 0; dq < D4; ++dq) {

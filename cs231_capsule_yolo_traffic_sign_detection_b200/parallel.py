@@ -27,6 +27,9 @@ def init_from_env(backend=None):
         kw = {}
         if use_cuda:
             kw['device_id'] = device
+        # a rank that leaves early must not hold its peers for NCCL's default 10 minutes
+        import datetime
+        kw['timeout'] = datetime.timedelta(seconds=int(os.environ.get('CAPS_DIST_TIMEOUT_S', '180')))
         dist.init_process_group(backend or ('nccl' if use_cuda else 'gloo'), rank=rank, world_size=world, **kw)
     return rank, world, device
 
