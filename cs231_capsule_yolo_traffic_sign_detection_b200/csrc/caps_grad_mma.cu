@@ -28,6 +28,7 @@ namespace caps {
 namespace {
 
 constexpr int kGmIT = 8;          // input capsules per CTA
+constexpr int kGmServiceWarps = 1;    // 1: one service warp fills the ring and sums the du fragments; 2: two warps -- measured SLOWER (9.3 vs 7.5 ms): ptxas budgets registers for 16 warps then (128 instead of 154)
 constexpr bool g_use_ffma2 = true;   // G build as 8 packed FMAs per term (scalar-broadcast coefficient) instead of 16 FFMA
 // Consumer warps (= output capsules) per CTA: 8 or 11.  11 + the producer warp = 384 threads is the most that still
 // leaves 168 registers per thread (X^m alone takes 16 M); three warps per scheduler instead of two hide more of the
@@ -137,7 +138,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // is far too little memory-level parallelism.
 // GEN = false: D == 16 exactly (the hot shapes): every dimension below is a compile-time constant.
 template <int M, int JW, bool GEN>
-__global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
+__global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(GradParams p) {
     const int pD = GEN ? p.D : 16, pDP = GEN ? p.DP : 16;
     constexpr int IT = kGmIT, DUB = gm_dub(JW), NT = 32 * JW;     // NT: consumer threads
     constexpr int NS = gm_stages(M, JW), SF = gm_stage_floats(M, JW);    // stage: u tile + up to M-1 coefficient rows
@@ -191,19 +192,21 @@ __global__ void __launch_bounds__(32 * JW + 32, 1) k_grad_mma(GradParams p) {
     }
     __syncthreads();
 
-    if (warp == JW) {
-        // ===== service warp: (1) one elected lane streams (tile, il) stages into the ring, NS ahead;
-        // (2) the whole warp sums the consumer warps' du fragments of each finished round and writes the CTA's
-        // partial -- so the consumers never meet at a CTA barrier.  Event loop over the two non-blocking waits.
+    if (warp >= JW) {
+        // ===== service warps: (1) warp JW: one elected lane streams (tile, il) stages into the ring, NS ahead;
+        // (2) warp JW + 1: sums the consumer warps' du fragments of each finished round and writes the CTA's partial --
+        // so the consumers never meet at a CTA barrier.  With kGmServiceWarps == 1 one warp does both in an event
+        // loop over the two non-blocking waits (the consumers then wait ~7 % of their time for a free du buffer).
+        const bool do_fill = warp == JW, do_reduce = warp == JW + kGmServiceWarps - 1;
         const uint32_t ubytes = 2 * 32 * 4 * 4, cbytes = (uint32_t)njr * 128u;
         int ncoef = 0;
 #pragma unroll
         for (int m = 0; m < M; ++m) ncoef += p.coef[m] != nullptr;
         const uint32_t txbytes = ubytes + (uint32_t)ncoef * cbytes;
-        int q = 0, ftile = 0, fil = 0;                      // next stage to fill
+        int q = 0, ftile = do_fill ? 0 : p.nbt, fil = 0;    // next stage to fill
         uint32_t ph = 1;
         const int rounds = p.nbt * (IT / DUB);
-        int rr = 0;                                         // next round to reduce
+        int rr = do_reduce ? 0 : rounds;                    // next round to reduce
         const int gg = lane >> 2, tt = lane & 3;
         const int kq = (2 * tt) >> 2, kk = (2 * tt) & 3;
         while (ftile < p.nbt || rr < rounds) {
@@ -401,7 +404,7 @@ int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
                         16 * gm_stages(M, JW) + 32;
     auto kern = pl.D == 16 ? k_grad_mma<M, JW, false> : k_grad_mma<M, JW, true>;
     if (pl.D == 16) CAPS_SET_SMEM(kern, smem); else CAPS_SET_SMEM(kern, smem);      // one cache per instantiation (and per device)
-    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * cdiv(pl.DP, 16), JW)), block(32 * JW + 32);
+    dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * cdiv(pl.DP, 16), JW)), block(32 * JW + 32 * kGmServiceWarps);
     kern<<<grid, block, smem, st>>>(gp);
     LAUNCH_CHECK();
     return 0;

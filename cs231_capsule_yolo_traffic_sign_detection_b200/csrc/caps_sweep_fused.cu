@@ -632,8 +632,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
                 // warp's tcgen05.ld behind that commit, so the accumulator barrier is not taken a second time
                 mbar_wait_i(base + kWsOffZfull + 8 * zs, ((uint32_t)m >> 3) & 1);
                 tc_fence_after();
-                uint32_t ur[16];
-                tmem_ld16_issue(lane_base + t * 128, ur);          // capsule 0's u_hat travels while Z is summed
+                uint32_t ur[32];
+                tmem_ld32_issue(lane_base + t * 128, ur);          // capsules 0 and 1 travel while Z is summed
                 const uint32_t zr = zr_base + zs * 4096;
                 float zz[kFsMaxCluster];
 #pragma unroll
@@ -657,10 +657,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
                     for (int jj = 0; jj < 4; ++jj) reinterpret_cast<float*>(cptr)[jj * kLanes] = f[jj];
                 }
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    if (jj > 0) tmem_ld16_issue(lane_base + t * 128 + jj * 16, ur);
-                    tmem_ld16_wait(ur);
-                    if (jj == 3) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (hh > 0) tmem_ld32_issue(lane_base + t * 128 + 32, ur);
+                    tmem_ld32_wait(ur);
+                    if (hh == 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -669,8 +669,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
                         }
                     }
 #pragma unroll
-                    for (int d = 0; d < 16; d += 2)
-                        ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], __uint_as_float(ur[d]), __uint_as_float(ur[d + 1]));
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        const int jj = hh * 2 + j2;
+#pragma unroll
+                        for (int d = 0; d < 16; d += 2)
+                            ffma2(acc[jj][d], acc[jj][d + 1], f[jj], f[jj], __uint_as_float(ur[j2 * 16 + d]), __uint_as_float(ur[j2 * 16 + d + 1]));
+                    }
                 }
                 cptr += cstep;
                 if (BWD) { st2 += kStageBytes; sb2 += 8; if (st2 == st_end) { st2 = 0; sb2 = 0; } }
