@@ -294,6 +294,22 @@ def main_gpu(args, rank, world, device):
     value = world * B / (ms_per_step * 1e-3)
     loss_val = float(loss)
 
+    # ---- the same step replayed from a CUDA graph (one launch instead of 17): matters where the step is launch-bound -----
+    graphed = None
+    if args.graph and world == 1:
+        try:
+            gs = pkg.GraphedStep(B, N, C, K, D, R, W)
+            gs.u.copy_(u); gs.y.copy_(y)
+            for _ in range(3):
+                gs.replay()
+            ms_g, _, _ = timed(gs.replay, args.steps)
+            graphed = {'ms_per_step': ms_g / args.steps, 'value': B / (ms_g / args.steps * 1e-3), 'unit': UNIT, 'loss': float(gs.loss),
+                       'what': 'forward + margin loss + backward captured once in a CUDA graph (GraphedStep), replayed per step'}
+            del gs
+            torch.cuda.empty_cache()
+        except Exception as e:
+            graphed = {'unavailable': repr(e)[:300]}
+
     # ---- end to end through the host-buffer C-ABI call ----------------------------------------
     # caps_host_pipe_*: every step copies ITS inputs host -> device (pinned memory) and its loss device -> host; the copy
     # of step n+1 is submitted before step n runs, so it overlaps the kernels (two device input slots)
@@ -451,6 +467,7 @@ def main_gpu(args, rank, world, device):
         'kernel_ms_per_step': per_class, 'profiled_ms_per_step': ms_prof / args.steps,
         'cpu_baseline': cpu,
         'eager_b200': eager,
+        'cuda_graph': graphed,
     }
     line.update(parity)
     print(json.dumps(line))
@@ -562,6 +579,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=64, help='micro-batch of the CPU baseline')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak (default): --batch per GPU; strong: --batch is the global batch, sharded over the GPUs')
+    ap.add_argument('--graph', action='store_true', help='also time the step replayed from a CUDA graph (N = 1)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-eager', action='store_true', help='skip the eager-reference-on-GPU leg')
     ap.add_argument('--eager-batch', type=int, default=256, help='micro-batch of the eager reference on the GPU')

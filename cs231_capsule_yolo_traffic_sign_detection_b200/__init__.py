@@ -8,8 +8,8 @@ The arithmetic lives in libcaps_routing.so (hand-written sm_100a CUDA, C ABI in
 include/caps_routing.h).  Importing the package does not need a GPU; running the routing branch
 does, and fails loudly without the built library -- there is no CPU fallback."""
 from . import _cabi
-from .capsule import (CapsuleLayer, HostPipe, HostStep, dark_capsule_loss, dark_regroup, dynamic_routing, primary_capsules, routing_margin_loss)
+from .capsule import (CapsuleLayer, GraphedStep, HostPipe, HostStep, dark_capsule_loss, dark_regroup, dynamic_routing, primary_capsules, routing_margin_loss)
 from .parallel import GradBucket, init_from_env, shard_bounds
 
-__all__ = ['CapsuleLayer', 'HostPipe', 'HostStep', 'dark_capsule_loss', 'dark_regroup', 'dynamic_routing', 'primary_capsules', 'routing_margin_loss',
+__all__ = ['CapsuleLayer', 'GraphedStep', 'HostPipe', 'HostStep', 'dark_capsule_loss', 'dark_regroup', 'dynamic_routing', 'primary_capsules', 'routing_margin_loss',
            'GradBucket', 'init_from_env', 'shard_bounds', '_cabi']

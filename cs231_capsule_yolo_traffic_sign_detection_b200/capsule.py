@@ -404,3 +404,59 @@ class HostStep:
                 _ptr(dW_dev), _ptr(self.scratch), self.scratch.numel(), B, N, C, K, D, R, _stream()),
                 'caps_route_step_host')
         return self.loss_host
+
+
+class GraphedStep:
+    """One routing train step -- forward, margin loss, fused backward: the 17 launches of caps_route_forward /
+    caps_margin_loss / caps_route_backward -- captured ONCE in a CUDA graph over static device buffers and replayed
+    with a single launch.  For the reference's own operating point (experiments/capsule/params.json: batch 64) the
+    step is launch-bound: the kernels are ~20 us each and the graph removes the gaps between them.
+
+        g = GraphedStep(B, N, C, K, D, n_iter, W)       # W [N,C,K,D] device tensor: read in place at every replay
+        g.u.copy_(u); g.y.copy_(y); g.replay()           # -> g.v, g.loss, g.du, g.dW
+    """
+
+    def __init__(self, B, N, C, K, D, n_iter, W, device=None):
+        L = _cabi.lib()
+        dev = W.device if device is None else torch.device(device)
+        self.dims = (B, N, C, K, D, n_iter)
+        self.W = W
+        self.u = torch.zeros(B, N, K, device=dev)
+        self.y = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.v = torch.empty(B, C, D, device=dev)
+        self.du = torch.empty(B, N, K, device=dev)
+        self.dW = torch.empty(N, C, K, D, device=dev)
+        self.loss = torch.empty((), device=dev)
+        self._lscr = torch.empty(_cabi.MARGIN_SCRATCH_FLOATS, device=dev)
+        nbytes = L.caps_route_workspace_bytes(B, N, C, K, D, n_iter, 1)
+        if nbytes == 0:
+            raise RuntimeError('unsupported dims %s' % (self.dims,))
+        self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._nbytes = nbytes
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.u.normal_()                      # warm-up on real-looking data (also sets the kernel attributes,
+                self._enqueue()                       # which must not happen inside a capture)
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(self.graph):
+                self._enqueue()
+
+    def _enqueue(self):
+        L = _cabi.lib()
+        B, N, C, K, D, R = self.dims
+        st = _stream()
+        _cabi.check(L.caps_route_forward(_ptr(self.u), _ptr(self.W), _ptr(self.v), None, _ptr(self._ws), self._nbytes,
+                                         B, N, C, K, D, R, 1, st), 'caps_route_forward')
+        _cabi.check(L.caps_margin_loss(_ptr(self.v), _ptr(self.y), 1.0 / B, _ptr(self.loss), None, _ptr(self._lscr), B, C, D, st),
+                    'caps_margin_loss')
+        _cabi.check(L.caps_route_backward(_ptr(self.u), _ptr(self.W), None, _ptr(self.y), 1.0 / B, None, _ptr(self.du), _ptr(self.dW),
+                                          _ptr(self._ws), self._nbytes, B, N, C, K, D, R, st), 'caps_route_backward')
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss

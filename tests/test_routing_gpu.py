@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_V = 1e-5
 TOL_G = 1e-4
-KNOB_DEFAULTS = {'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'c1': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
+KNOB_DEFAULTS = {'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'fsws': 1, 'c1': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
 
 
 @pytest.fixture(autouse=True)
@@ -223,8 +223,15 @@ def test_fused_sweep_matches_unfused_and_oracle(capsb, dims):
         assert_close_elementwise(res[fused]['du'], ref['du'], what='du fused=%d' % fused)
     for k in ('v', 'c', 'du', 'dW'):
         assert rel_err(res[1][k], res[0][k]) < 5e-6, k
-    # i-split of the fused sweep only regroups the sum over input capsules
+    # the two epilogue organisations of the fused sweep (8 logit + 8 accumulate warps / 8 warps doing both) run the
+    # same arithmetic in the same order
     capsb._cabi.set_tuning('fused', 1)
+    capsb._cabi.set_tuning('fsws', 0)
+    old_epi = cuda_step(capsb, u, W, y, R)
+    capsb._cabi.set_tuning('fsws', 1)
+    for k in ('v', 'c', 'du', 'dW'):
+        assert rel_err(old_epi[k], res[1][k]) < 5e-6, k
+    # i-split of the fused sweep only regroups the sum over input capsules
     capsb._cabi.set_tuning('isplit', 2)
     alt = cuda_step(capsb, u, W, y, R)
     for k in ('v', 'du', 'dW'):
@@ -674,3 +681,28 @@ def test_capsnet_cfg1_end_to_end(capsb):
     assert rel_err(pw[::st].cpu().numpy(), g['prim_w_probe']) < tol
     assert rel_err(pb.cpu().numpy(), g['prim_b']) < tol
     assert rel_err(digits.route_weights.grad.reshape(-1)[::st * 11].cpu().numpy(), g['route_w_probe']) < tol
+
+
+@pytest.mark.gpu
+def test_cuda_graph_step_matches_plain_calls(capsb):
+    """GraphedStep (forward + margin loss + backward captured in one CUDA graph) replays to the same bits as the plain
+    calls, for two different batches fed through its static buffers, and matches the fp64 oracle."""
+    from oracle import routing_c as oc
+    from oracle import routing_np as onp
+    B, N, C, K, D, R = 64, 96, 43, 8, 16, 3
+    dev = torch.device('cuda')
+    u0, W, y0 = onp.make_inputs(B, N, C, K, D, seed=5)
+    Wt = torch.from_numpy(W).to(dev)
+    g = capsb.GraphedStep(B, N, C, K, D, R, Wt)
+    for seed in (5, 6):
+        u, _, y = onp.make_inputs(B, N, C, K, D, seed=seed)
+        g.u.copy_(torch.from_numpy(u)); g.y.copy_(torch.from_numpy(y))
+        g.replay()
+        torch.cuda.synchronize()
+        plain = cuda_step(capsb, u, W, y, R, want_c=False)
+        assert np.array_equal(g.v.cpu().numpy(), plain['v'])
+        assert np.array_equal(g.du.cpu().numpy(), plain['du'])
+        assert np.array_equal(g.dW.cpu().numpy(), plain['dW'])
+        assert float(g.loss) == plain['loss']
+        ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R, want_c=False)
+        assert rel_err(g.v.cpu().numpy(), ref['v']) < 1e-5 and rel_err(g.dW.cpu().numpy(), ref['dW']) < 1e-4

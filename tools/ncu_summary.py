@@ -1,7 +1,7 @@
 """Turns an `ncu --set full` report into the per-kernel table and the traffic file bench.py reads.
 
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > /tmp/raw.csv      (done by this script)
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_ncu_summary.md profiles/r1_ncu_traffic.json
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r2_ncu_summary.md profiles/r2_ncu_traffic.json 'title' batch=8192,n_nodes=1152,n_caps=43
 
 One row per kernel (template arguments kept), means over its launches.
 """
@@ -65,8 +65,23 @@ def main():
                 a['fma'] / n, a['smem'] / n, a['dram_rd'] / n / 1e9, a['dram_wr'] / n / 1e9, (a['dram_pct'] + a['dram_pct_w']) / n, a['inst'] / n / 1e6))
     kern = {k: {'dram_bytes_per_launch': (a['dram_rd'] + a['dram_wr']) / a['n'], 'time_ms_under_ncu': a['time_ms'] / a['n'],
                 'launches': int(a['n'])} for k, a in agg.items()}
-    json.dump({'source': '%s (ncu --set full --clock-control none), via tools/ncu_summary.py' % out_md, 'title': title, 'kernels': kern},
-              open(out_json, 'w'), indent=1)
+    # bench.py's kernel classes (KCLASS indices) -> measured DRAM bytes per launch, averaged over the class's launches
+    cls_of = [(1, 'k_pass_tc<0'), (2, 'k_pass_tc<1'), (3, 'k_pass_tc<2'), (10, 'k_sweep_fused'), (6, 'k_grad'), (11, 'k_c1_')]
+    by_cls = {}
+    for cid, prefix in cls_of:
+        tot = sum((a['dram_rd'] + a['dram_wr']) for k, a in agg.items() if k.startswith(prefix))
+        cnt = sum(a['n'] for k, a in agg.items() if k.startswith(prefix))
+        if cnt:
+            by_cls[str(cid)] = tot / cnt
+    step_total = sum(a['dram_rd'] + a['dram_wr'] for a in agg.values())
+    dims = {}
+    for kv in (sys.argv[5].split(',') if len(sys.argv) > 5 else []):      # e.g. batch=8192,n_nodes=1152,n_caps=43
+        k, v = kv.split('=')
+        dims[k] = int(v)
+    out = {'source': '%s (ncu --set full --clock-control none), via tools/ncu_summary.py' % out_md, 'title': title}
+    out.update(dims)
+    out.update({'dram_bytes_all_captured_launches': step_total, 'dram_bytes_per_launch_by_class': by_cls, 'kernels': kern})
+    json.dump(out, open(out_json, 'w'), indent=1)
     print(open(out_md).read())
 
 
