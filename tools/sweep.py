@@ -71,8 +71,8 @@ def main():
     print('|---|---|---|---|---|---|---|---|---|---|---|')
     for name, B, N, C, D, R in rows:
         ms, sps, tf, gib = time_step(B, N, C, D, R)
-        eng = ('tcgen05 + mma.sync' if (D > 8 and C >= 7) else 'tcgen05 passes + fp32 FMA gradient sweep' if (D > 8 and C >= 2)
-               else 'fp32 FMA')
+        eng = ('fused cluster sweep (tcgen05) + mma.sync' if (D > 8 and D <= 16 and C >= 7 and C <= 64 and R > 1) else 'tcgen05 + mma.sync' if (D > 8 and C >= 7) else 'tcgen05 passes + fp32 FMA gradient sweep' if (D > 8 and C >= 2)
+               else 'single-capsule kernels' if C == 1 else 'fp32 FMA')
         print('| %s | %d | %d | %d | %d | %d | %s | %.3f | %.0f | %.2f | %.2f |' % (name, B, N, C, D, R, eng, ms, sps, tf, gib))
         sys.stdout.flush()
 
