@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- capsule-routing samples/sec, fwd+bwd, on N B200s (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--workload cfg2|cfg1|cfg3|cfg3_head]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--scaling weak|strong] [--graph]
+                    [--workload cfg2|cfg1|cfg3|cfg3_head]
 
 A "step" is one pass of the hot path over one batch of synthetic input: routing forward
 (reference models.py:70-79), margin loss (loss_fns.py:12-17,23), backward to du and dW
@@ -12,8 +13,8 @@ batch with no data-path collective and average dW with one NCCL all-reduce per s
 Prints ONE JSON line (rank 0).  `value` times K steps with inputs resident in HBM (CUDA events,
 max over ranks); `e2e` times the same K steps through the host-buffer C-ABI call
 (caps_route_step_host: H2D of u,y from pinned memory and D2H of the loss inside the timed region);
-`roofline` is for the dominant kernel (the pass kernel) from CUDA events recorded around every
-launch in the timed region; `cpu_baseline` / `--impl reference` time the UNMODIFIED reference layer (baseline/_ref, brought along by
+`roofline` is for the dominant kernel class (the gradient sweep, or the fused sweeps) from CUDA events recorded
+around every launch in a second run of the same K steps; `cpu_baseline` / `--impl reference` time the UNMODIFIED reference layer (baseline/_ref, brought along by
 baseline/install_reference.py; `kind: "reference"`) on this box's host cores over a bounded sample -- or the
 oracle's op-for-op torch port (`kind: "port"`) when the reference is not installed.  `eager_b200` is the same
 unmodified reference run eagerly on the B200 (informational second baseline).  After the timed region a 64-sample
@@ -429,8 +430,9 @@ def main_gpu(args, rank, world, device):
     binds = {6: 'shared-memory pipe and issue slots, not HBM and not the tensor pipe (ncu, profiles/): both products have one side '
                 'only 8 wide and need fp32-grade accuracy (3xTF32), the G operand is built per sample on the FMA pipe and has to '
                 'cross shared memory to reach both fragment layouts; tools/probe_tc2.cu + DESIGN.md 3.3 say why tcgen05 does not help',
-             10: 'issue slots of the 8 epilogue warps (ncu: ~200 instructions per warp and input capsule at ~40 % issue '
-                 'efficiency with two warps per scheduler); tensor pipe ~20 % busy, DRAM < 10 %',
+             10: 'latency of the loop MMA -> logit warps -> cluster exchange -> accumulate warps -> free accumulator (4 TMEM '
+                 'accumulators; one cluster-wide synchronisation per stage); ncu: issue slots ~55 % busy, tensor pipe 21-24 %, '
+                 'FMA pipe 25-27 %, DRAM 20-36 % (profiles/r2_ncu_summary.md, r2_analysis.md)',
              11: 'HBM (u is read twice and du written once; nothing else is large)'}
     roofline['binds'] = binds.get(dom, 'see DESIGN.md section 5')
     roofline_other = {KCLASS[c]: roof(c) for c in cand if c != dom}

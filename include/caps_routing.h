@@ -166,7 +166,7 @@ int caps_route_step_host(const float* u_host, const int64_t* y_host, const float
  *   submit    enqueues the H2D copy of one batch (u_host [B,N,K], y_host [B] int64; HOST, pinned for overlap) into
  *             the free slot; at most two batches may be submitted and not yet stepped (CAPS_E_STATE otherwise)
  *   step      waits for the oldest submitted batch, runs forward + margin loss + fused backward on `stream`
- *             (du is not produced: no backbone below this entry point), copies the loss (and v if non-NULL) to the
+ *             (du is computed like in any backward and stays in the pipe's device scratch), copies the loss (and v if non-NULL) to the
  *             host and synchronises `stream`.  dw_ready_event as in caps_route_backward_ev.
  * Typical loop:  submit(b0); for n: { submit(b[n+1]); step(...); }   A pipe belongs to one host thread at a time. */
 size_t caps_host_pipe_scratch_bytes(int B, int N, int C, int K, int D, int R);
@@ -196,6 +196,8 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
  *   name = "fused" 1 (default): one cluster-fused sweep per routing iteration (logits -> softmax -> weighted sum, and
  *                 its backward counterpart) where it applies (9 <= D <= 16, 4 <= C <= 64); 0: three kernels per iteration
  *                 with max-subtracted softmax (the fused sweep exponentiates logits directly: |logit| must stay < 80)
+ *   name = "fsws" 1 (default): warp-specialised epilogue of the fused sweep (8 logit warps + 8 accumulate warps per CTA);
+ *                 0: 8 epilogue warps doing both halves (the round-2 first version; same arithmetic, same order)
  *   name = "c1"   1 (default): dedicated GEMM + squash kernels for a single class capsule (C == 1, D <= 8); 0: general kernels
  *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
