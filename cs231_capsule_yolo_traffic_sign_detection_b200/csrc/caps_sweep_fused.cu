@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
             asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
             const bool has_beta = BWD && p.beta_in != nullptr;
             const bool do_store = tvalid && p.coef_out != nullptr && !(p.dbg & 2);             // warp-uniform
+            const bool more_than_6 = p.JG > 6;
             float acc[4][16];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
@@ -637,8 +638,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_sweep_fused_ws(FusedParams p)
                 const uint32_t zr = zr_base + zs * 4096;
                 float zz[kFsMaxCluster];
 #pragma unroll
-                for (int r = 0; r < kFsMaxCluster; ++r) zz[r] = lds_f32(zr + r * 512);
-                const float Z = ((zz[0] + zz[1]) + (zz[2] + zz[3])) + ((zz[4] + zz[5]) + (zz[6] + zz[7]));    // fixed order: same bits in every CTA
+                for (int r = 0; r < 6; ++r) zz[r] = lds_f32(zr + r * 512);
+                // rows of absent ranks are exact zeros: with <= 6 CTAs per cluster (C <= 48) their loads and adds are skipped,
+                // (z4 + z5) + 0 == z4 + z5 bit for bit, so both branches give every CTA the same Z
+                float z67 = 0.f;
+                if (more_than_6) z67 = lds_f32(zr + 6 * 512) + lds_f32(zr + 7 * 512);
+                const float Z = ((zz[0] + zz[1]) + (zz[2] + zz[3])) + ((zz[4] + zz[5]) + z67);    // fixed order: same bits in every CTA
                 float f[4];
                 const float rz = BWD ? 0.f : rcp_approx(Z);
 #pragma unroll
