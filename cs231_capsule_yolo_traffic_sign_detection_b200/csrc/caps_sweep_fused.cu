@@ -765,13 +765,29 @@ int launch_k(const Plan& pl, const FusedParams& fp, int IS, bool bwd, bool ws, c
 int g_fs_dbg = 0;
 int g_fs_ws = 1;         // tuning knob "fsws": 1 = warp-specialised epilogue (8 logit warps + 8 accumulate warps), 0 = 8 warps doing both
 
+// The warp-specialised kernel re-partitions its register pool with setmaxnreg: 256 threads x 104 + 256 x 112 + 128 x 48 =
+// 640 x 96.  That only adds up if ptxas gave the kernel exactly 96 registers per thread at launch; with fewer, an
+// `inc` would wait for registers that never come.  Checked once per process; otherwise the 8-warp kernel runs.
+bool fs_use_ws() {
+    if (g_fs_ws == 0) return false;
+    static const bool ok = [] {
+        cudaFuncAttributes a0{}, a1{};
+        if (cudaFuncGetAttributes(&a0, k_sweep_fused_ws<false>) != cudaSuccess || cudaFuncGetAttributes(&a1, k_sweep_fused_ws<true>) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a0.numRegs >= 96 && a1.numRegs >= 96;
+    }();
+    return ok;
+}
+
 // D == 16 (after padding), 8 capsules per CTA, one cluster of ceil(C/8) <= 8 CTAs per (128 samples, i range)
 bool fused_shape_ok(int C, int DP, bool tc_ok) { return tc_ok && DP == 16 && cdiv(C, 8) <= kFsMaxCluster; }
 bool fused_supported(const Plan& pl) { return pl.use_tc && pl.Reff > 1 && fused_shape_ok(pl.C, pl.DP, pl.tc_ok); }
 
 // clusters of `jg` CTAs the device can run at once (GPC granularity: not simply SMs / jg)
 int fused_cluster_capacity(int jg, bool bwd) {
-    const bool ws = g_fs_ws != 0;
+    const bool ws = fs_use_ws();
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || jg < 1 || jg > kFsMaxCluster) return 0;
     std::atomic<int>& slot = g_cap[ws ? 1 : 0][bwd ? 1 : 0].n[dev][jg];
@@ -822,7 +838,7 @@ int launch_sweep_fused(const Plan& pl, bool bwd, const float* ua, const float* w
     fp.ua = ua; fp.wb = wb; fp.X = X; fp.coef_in = coef_in; fp.beta_in = beta_in; fp.coef_out = coef_out; fp.part = part;
     fp.N = pl.N; fp.C = pl.C; fp.JG = cdiv(pl.C, 8); fp.nbt = pl.nbt;
     fp.i_per_split = cdiv(cdiv(pl.N, IS), 4) * 4;
-    const bool ws = g_fs_ws != 0;
+    const bool ws = fs_use_ws();
     fp.ns = fs_stages(bwd, ws);
     fp.dbg = g_fs_dbg;
     if (cdiv(pl.N, fp.i_per_split) != IS) return fail(CAPS_E_BADARG, "fused sweep: %d splits do not tile N=%d", IS, pl.N);
