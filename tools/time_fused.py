@@ -34,6 +34,7 @@ def step():
     _cabi.check(L.caps_route_backward(P(u), P(W), None, P(y), 1.0 / B, None, P(du), P(dW), P(ws), nbytes, B, N, C, K, D, R, st), 'bwd')
 
 
+ref = None
 for setting in settings:
     for kv in setting.split(','):
         k, val = kv.split('=')
@@ -49,9 +50,14 @@ for setting in settings:
     e1.record()
     torch.cuda.synchronize()
     total = e0.elapsed_time(e1) / NREP
+    if ref is None:
+        ref = (v.clone(), du.clone(), dW.clone())
+        dev_s = ''
+    else:       # deviation from the first setting's results (max-norm relative): 0 = same bits
+        dev_s = ' | vs first: ' + ' '.join('%s %.1e' % (nm, float((a - b).abs().max() / b.abs().max())) for nm, a, b in zip(('v', 'du', 'dW'), (v, du, dW), ref))
     _cabi.set_tuning('profile', 1)
     step()
     ms = (ctypes.c_double * len(KCLASS))(); n = (ctypes.c_long * len(KCLASS))()
     _cabi.check(L.caps_profile_collect(ms, n, len(KCLASS)), 'profile')
     _cabi.set_tuning('profile', 0)
-    print('%-28s step %.3f ms | ' % (setting, total) + ' '.join('%s %.3f/%d' % (KCLASS[i], ms[i], n[i]) for i in range(len(KCLASS)) if n[i]), flush=True)
+    print('%-28s step %.3f ms | ' % (setting, total) + ' '.join('%s %.3f/%d' % (KCLASS[i], ms[i], n[i]) for i in range(len(KCLASS)) if n[i]) + dev_s, flush=True)
