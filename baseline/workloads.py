@@ -109,6 +109,24 @@ def make_cfg1_step(device, dropin=False):
     return step, model
 
 
+def make_cfg1_epoch(device, batch, graph=False):
+    """configs[0] through the sync-free side runner (package runner.py): the same model, loss and
+    optimizer as make_cfg1_step(dropin=True), but a whole epoch of batches per call -- staged copies one batch ahead,
+    no per-step host synchronisation.  Returns epoch(x_np, y_np) -> avg_loss."""
+    ref = refload.load()
+    if ref is None:
+        raise RuntimeError('reference not installed (baseline/_ref)')
+    import cs231_capsule_yolo_traffic_sign_detection_b200 as pkg
+    params = refload.make_params(ref, 'capsule', str(device), recon=True)
+    params.batch_size = batch
+    model = _build(ref, 'CapsuleNet', params, device, pkg.CapsuleLayer)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-3, capturable=graph)
+
+    def epoch(x_np, y_np):
+        return pkg.runner.train(x_np, y_np, model, opt, ref.loss_fns.capsule_loss, None, params, no_metric=True, shuffle=False, graph=graph)[0]
+    return epoch
+
+
 def make_cfg3_step(device, dropin=False, fused_tail=False, grid=7, world=1):
     """BASELINE.json configs[2]: DarkCapsuleNet train step with `--recon --no_metric` semantics (reference
     main.py:55-77, models.py:389-400, loss_fns.py:187-204).  fused_tail: the cell regroup and the loss run as

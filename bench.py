@@ -534,6 +534,24 @@ def main_model(args, rank, world, device):
         out[name] = {'samples_per_s': world * B / sec, 'ms_per_step': sec * 1e3, 'loss': loss}
         del step
         torch.cuda.empty_cache()
+    if cfg == 'cfg1' and world == 1:
+        # the same step through the sync-free side runner: an epoch of `steps` batches per call;
+        # graphed: every step replayed from one CUDA graph (forward, loss, backward, Adam)
+        import numpy as np
+        for name, graph in (('dropin_syncfree_runner', False), ('dropin_graphed_runner', True)):
+            epoch = workloads.make_cfg1_epoch(device, B, graph=graph)
+            epoch(np.concatenate([x] * max(args.warmup, 3)), np.concatenate([y] * max(args.warmup, 3)))
+            xe, ye = np.concatenate([x] * args.steps), np.concatenate([y] * args.steps)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            avg = epoch(xe, ye)
+            torch.cuda.synchronize()
+            sec = (time.perf_counter() - t0) / args.steps
+            out[name] = {'samples_per_s': B / sec, 'ms_per_step': sec * 1e3, 'loss': avg,
+                         'what': 'runner.train: main.py:38-95 with staged copies and one host synchronisation per epoch instead of three per step'
+                                 + ('; every step replayed from one CUDA graph' if graph else '')}
+            del epoch
+            torch.cuda.empty_cache()
     if rank != 0:
         return 0
     cpu = None

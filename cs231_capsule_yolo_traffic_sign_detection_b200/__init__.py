@@ -10,6 +10,7 @@ does, and fails loudly without the built library -- there is no CPU fallback."""
 from . import _cabi
 from .capsule import (CapsuleLayer, GraphedStep, HostPipe, HostStep, dark_capsule_loss, dark_regroup, dynamic_routing, primary_capsules, routing_margin_loss)
 from .parallel import GradBucket, init_from_env, shard_bounds
+from . import runner
 
 __all__ = ['CapsuleLayer', 'GraphedStep', 'HostPipe', 'HostStep', 'dark_capsule_loss', 'dark_regroup', 'dynamic_routing', 'primary_capsules', 'routing_margin_loss',
-           'GradBucket', 'init_from_env', 'shard_bounds', '_cabi']
+           'GradBucket', 'init_from_env', 'shard_bounds', 'runner', '_cabi']
