@@ -427,12 +427,16 @@ def main_gpu(args, rank, world, device):
     cand = [c for c in cls_bytes if n_cls[c]]
     dom = max(cand, key=lambda c: ms_cls[c])
     roofline = roof(dom)
-    binds = {6: 'shared-memory pipe and issue slots, not HBM and not the tensor pipe (ncu, profiles/): both products have one side '
-                'only 8 wide and need fp32-grade accuracy (3xTF32), the G operand is built per sample on the FMA pipe and has to '
-                'cross shared memory to reach both fragment layouts; tools/probe_tc2.cu + DESIGN.md 3.3 say why tcgen05 does not help',
-             10: 'latency of the loop MMA -> logit warps -> cluster exchange -> accumulate warps -> free accumulator (4 TMEM '
-                 'accumulators; one cluster-wide synchronisation per stage); ncu: issue slots ~55 % busy, tensor pipe 21-24 %, '
-                 'FMA pipe 25-27 %, DRAM 20-36 % (profiles/r2_ncu_summary.md, r2_analysis.md)',
+    binds = {6: 'instruction issue latency, not HBM and not the tensor pipe: 11 + 1 warps per SM is what the register file holds '
+                '(80 registers of per-sample state per thread), every warp is a stream of short dependent steps (~200 '
+                'instructions per 32-sample unit, a third of them the tf32 hi/lo splits of the 3xTF32 products); ncu: issue 45 %, '
+                'shared-memory pipe 56-63 %, legacy HMMA pipe 30 %; timing probes with all of G\'s shared-memory traffic off (-2 %), '
+                'shorter HMMA chains and a software-pipelined G build (slower) rule the other candidates out '
+                '(profiles/r2_analysis.md); tools/probe_tc2.cu + DESIGN.md 3.3 say why tcgen05 does not help',
+             10: 'the instruction stream of the 8 logit + 8 accumulate warps per CTA (1966 warp instructions per 128-sample x '
+                 '8-capsule stage, ~950 cycles); ncu: issue slots ~55 % busy, FMA pipe 42 % of cycles, tensor pipe 21-24 %, DRAM '
+                 '20-36 %; a scratch build without the cluster exchange is no faster, so the per-stage cluster synchronisation '
+                 'is not on the critical path (profiles/r2_ncu_summary.md, r2_analysis.md)',
              11: 'HBM (u is read twice and du written once; nothing else is large)'}
     roofline['binds'] = binds.get(dom, 'see DESIGN.md section 5')
     roofline_other = {KCLASS[c]: roof(c) for c in cand if c != dom}
