@@ -21,10 +21,12 @@ values, that a caller may use instead of `main.train` / `main.evaluate`:
     allocate on the device, so the unchanged loss function is capturable.
 
 On a CPU device the runner degrades to the reference's loop order without streams (used by the CPU tests)."""
+import weakref
+
 import numpy as np
 import torch
 
-__all__ = ['train', 'evaluate']
+__all__ = ['train', 'evaluate', 'reset_graphs']
 
 MAX_METRIC_SAMPLES = 1000      # config.py:53 (config.max_metric_samples)
 
@@ -135,11 +137,23 @@ _EAGER_STEPS_BEFORE_CAPTURE = 2
 
 
 def _graph_cache(model, optimizer, training):
-    """graphs live as long as the model: {(batch size, optimizer id, training): _GraphedStep | eager-step count}"""
-    cache = model.__dict__.setdefault('_caps_runner_graphs', {})
+    """Graphs live as long as the model and belong to ONE optimizer object: {(batch size, training): _GraphedStep or the
+    number of eager steps taken so far}.  A different optimizer (or none after one) starts over -- a captured step
+    updates the state tensors of the optimizer it was captured with.  Parameters must stay where they are (in-place
+    `load_state_dict` is fine; `model.to(...)` / re-created parameters need `reset_graphs(model)`)."""
     if training and not all(g.get('capturable', False) for g in optimizer.param_groups):
         raise ValueError('runner: graph=True needs an optimizer built with capturable=True (its step counter must live on the device)')
-    return cache
+    slot = model.__dict__.get('_caps_runner_graphs')
+    owner = slot['optimizer']() if slot is not None and slot['optimizer'] is not None else None
+    if slot is None or (training and owner is not optimizer):
+        slot = {'optimizer': weakref.ref(optimizer) if optimizer is not None else (slot['optimizer'] if slot else None), 'steps': {}}
+        model.__dict__['_caps_runner_graphs'] = slot
+    return slot['steps']
+
+
+def reset_graphs(model):
+    """Drops the CUDA graphs `train` / `evaluate(graph=True)` captured for this model."""
+    model.__dict__.pop('_caps_runner_graphs', None)
 
 
 def _epoch(x, y, model, optimizer, loss_fn, params, training, graph=False):
@@ -157,7 +171,7 @@ def _epoch(x, y, model, optimizer, loss_fn, params, training, graph=False):
     for i in range(n_batch):
         stager.submit(i + 1)
         x_bch, y_bch = stager.take(i)
-        key = (x_bch.shape[0], id(optimizer), training)
+        key = (x_bch.shape[0], training)
         step = cache.get(key, 0) if cache is not None else 0
         if cache is not None and step == _EAGER_STEPS_BEFORE_CAPTURE:
             step = cache[key] = _GraphedStep(model, optimizer, loss_fn, params, use_recon, training, x_bch, y_bch)

@@ -115,8 +115,15 @@ def test_graphed_runner_matches_eager_runner():
         lg = pkg.runner.train(x, y, m_g, o_g, loss_fn, metric, params, shuffle=False, graph=True)[0]
         assert abs(lg - le) <= 1e-6 * abs(le), (epoch, lg, le)
         assert np.allclose(preds[-1], preds[-2], rtol=1e-5, atol=1e-7)
-    assert any(isinstance(v, pkg.runner._GraphedStep) for v in m_g._caps_runner_graphs.values())
+    assert any(isinstance(v, pkg.runner._GraphedStep) for v in m_g._caps_runner_graphs['steps'].values())
     for a, b in zip(m_e.parameters(), m_g.parameters()):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7)
     with pytest.raises(ValueError):
         pkg.runner.train(x, y, m_g, torch.optim.Adam(m_g.parameters()), loss_fn, metric, params, graph=True)
+    # a different optimizer object starts over: its graphs are captured against its own state tensors
+    o2 = torch.optim.Adam(m_g.parameters(), lr=1e-3, capturable=True)
+    pkg.runner.train(x[:30], y[:30], m_g, o2, loss_fn, metric, params, shuffle=False, graph=True)
+    assert m_g._caps_runner_graphs['optimizer']() is o2
+    assert not any(isinstance(v, pkg.runner._GraphedStep) for v in m_g._caps_runner_graphs['steps'].values())   # 2 batches of 15: still eager
+    pkg.runner.reset_graphs(m_g)
+    assert '_caps_runner_graphs' not in m_g.__dict__
