@@ -293,6 +293,7 @@ int caps_set_tuning(const char* name, int value) {
     if (!strcmp(name, "tc")) { g_tune_tc = value != 0; return 0; }
     if (!strcmp(name, "fused")) { g_tune_fused = value != 0; return 0; }
     if (!strcmp(name, "c1")) { g_tune_c1 = value != 0; return 0; }
+    if (!strcmp(name, "c1v")) { if (value != 1 && value != 2) return fail(CAPS_E_BADARG, "c1v must be 1 or 2"); g_c1_version = value; return 0; }
     if (!strcmp(name, "isplit")) {
         if (value < 0 || value > kMaxSplits) return fail(CAPS_E_BADARG, "isplit must be in [0,%d]", kMaxSplits);
         g_tune_isplit = value;
@@ -452,9 +453,9 @@ int caps_route_backward_ev(const float* u, const float* W, const float* grad_v, 
         if (!u) return fail(CAPS_E_BADARG, "caps_route_backward: u is required for a single class capsule");
         float* w1 = static_cast<float*>(ws);
         int nl = 0, rc1;
-        g_launches.fetch_add(1, std::memory_order_relaxed);       // two launches inside: count the second one here
         { LaunchScope ls_(kcC1, st); rc1 = launch_c1_backward(u, W, w1 + pl.o_s, grad_v, y, margin_scale, loss_grad_dev, du, dW,
                                                               w1 + pl.o_dupart, B, N, K, D, st, &nl); }
+        if (nl > 1) g_launches.fetch_add(nl - 1, std::memory_order_relaxed);      // the scope counted one launch
         if (!rc1 && dw_ready_event) CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(dw_ready_event), st));
         return rc1;
     }

@@ -78,6 +78,7 @@ int launch_sweep_fused(const Plan& pl, bool bwd, const float* ua, const float* w
                        const float* beta_in, float* coef_out, float* part, int IS, cudaStream_t st);
 int launch_coef_public(const Plan& pl, const float* coef, int CS, float* c_pub, cudaStream_t st);
 // caps_c1.cu: one class capsule (the DarkCapsuleNet head): the layer is one skinny GEMM + squash
+extern int g_c1_version;                   // tuning knob "c1v"
 bool c1_supported(int N, int C, int K, int D);
 size_t c1_part_floats(int B, int N, int K, int D);
 int launch_c1_forward(const float* u, const float* W, float* v, float* s_save, int B, int N, int K, int D, cudaStream_t st);

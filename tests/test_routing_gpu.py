@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_V = 1e-5
 TOL_G = 1e-4
-KNOB_DEFAULTS = {'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'fsws': 1, 'c1': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
+KNOB_DEFAULTS = {'c1v': 2, 'spt': 0, 'isplit': 0, 'tc': 1, 'fused': 1, 'fsws': 1, 'c1': 1, 'gradmma': 1, 'gradjw': 0, 'hostmb': 0, 'sbstaged': 1, 'tcstages': 10}
 
 
 @pytest.fixture(autouse=True)
@@ -323,6 +323,7 @@ def test_backward_validates_forward_state(capsb):
     (7, 512, 1, 8, 5, 1),         # odd batch (the forward kernel takes samples in pairs), one iteration
     (33, 24, 1, 8, 8, 2),         # D = 8, N*8 smaller than one pass of the thread block
     (20, 100, 1, 8, 3, 3),
+    (4100, 12, 1, 8, 5, 2),       # more samples than one shared-memory chunk of ds in the backward kernel (4096)
 ])
 def test_single_capsule_head_kernels(capsb, dims):
     """One class capsule (reference models.py:368-370): the dedicated GEMM + squash kernels (caps_c1.cu) against the
@@ -335,8 +336,9 @@ def test_single_capsule_head_kernels(capsb, dims):
     gext = (np.random.default_rng(3).standard_normal((B, C, D)) * 0.05).astype(np.float32)
     ref = oc.routing_step(u.astype(np.float64), W.astype(np.float64), y, R, grad_v_extra=gext.astype(np.float64))
     res = {}
-    for c1 in (1, 0):
-        capsb._cabi.set_tuning('c1', c1)
+    for c1 in (2, 1, 0):                # 2 / 1: the two generations of the dedicated kernels (knob c1v), 0: the general kernels
+        capsb._cabi.set_tuning('c1', 1 if c1 else 0)
+        capsb._cabi.set_tuning('c1v', c1 if c1 else 2)
         res[c1] = cuda_step(capsb, u, W, y, R, grad_v_extra=gext)
         assert rel_err(res[c1]['v'], ref['v']) < TOL_V, c1
         assert np.array_equal(res[c1]['c'], np.ones((B, N, 1), np.float32))
@@ -346,7 +348,13 @@ def test_single_capsule_head_kernels(capsb, dims):
         assert_close_elementwise(res[c1]['dW'], ref['dW'], what='dW c1=%d' % c1)
     for k in ('v', 'du', 'dW'):
         assert rel_err(res[1][k], res[0][k]) < 5e-6, k
-    again = cuda_step(capsb, u, W, y, R, grad_v_extra=gext)          # c1 = 0 still set: fixed summation order either way
+        assert rel_err(res[2][k], res[0][k]) < 5e-6, k
+    capsb._cabi.set_tuning('c1', 1)
+    twice = cuda_step(capsb, u, W, y, R, grad_v_extra=gext)         # second generation again: fixed summation order
+    for k in ('v', 'du', 'dW'):
+        assert np.array_equal(twice[k], res[2][k]), k
+    capsb._cabi.set_tuning('c1', 0)
+    again = cuda_step(capsb, u, W, y, R, grad_v_extra=gext)          # c1 = 0: fixed summation order either way
     for k in ('v', 'du', 'dW'):
         assert np.array_equal(again[k], res[0][k]), k
 
