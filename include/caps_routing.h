@@ -199,6 +199,8 @@ int caps_fma_peak(int iters, float* ms_out, double* flops_out, void* stream);
  *   name = "fsws" 1 (default): warp-specialised epilogue of the fused sweep (8 logit warps + 8 accumulate warps per CTA);
  *                 0: 8 epilogue warps doing both halves (the round-2 first version; same arithmetic, same order)
  *   name = "c1"   1 (default): dedicated GEMM + squash kernels for a single class capsule (C == 1, D <= 8); 0: general kernels
+ *   name = "c1v"  which generation of those kernels: 2 (default) two launches per forward + backward, no dW partials;
+ *                 1 the first generation (three launches), kept as a cross-check
  *   name = "tcstages" shared-memory ring depth of the tcgen05 pass kernel, 2..12 (default 10)
  *   name = "gradmma" 1 (default): tensor-core (mma.sync 3xTF32) gradient kernel where it applies
  *                 (D >= 9, C >= 7); 0: fp32-FMA gradient kernel everywhere
