@@ -553,7 +553,11 @@ int caps_margin_loss(const float* v, const int64_t* y, float scale, float* loss,
     int blocks = scratch ? (int)((n + 1023) / 1024) : 1;        // ~4 (b,j) rows per thread
     if (blocks > CAPS_MARGIN_SCRATCH_FLOATS) blocks = CAPS_MARGIN_SCRATCH_FLOATS;
     if (blocks < 1) blocks = 1;
-    { LaunchScope ls_(kcLoss, st); k_margin_loss<<<blocks, 256, 0, st>>>(v, y, scale, loss, scratch, scores_out, B, C, D); }
+    // small problems (the DarkCapsuleNet head: 1568 rows): ONE block of 1024 threads, no second launch -- the kernel is
+    // a latency chain of a few dependent loads per thread, so fewer rows per thread and one launch less is all that counts
+    const int threads = n <= 4096 ? 1024 : 256;
+    if (n <= 4096) blocks = 1;
+    { LaunchScope ls_(kcLoss, st); k_margin_loss<<<blocks, threads, 0, st>>>(v, y, scale, loss, scratch, scores_out, B, C, D); }
     LAUNCH_CHECK();
     if (blocks > 1) {
         { LaunchScope ls_(kcLoss, st); k_margin_loss_final<<<1, 256, 0, st>>>(scratch, blocks, scale, loss); }
@@ -636,8 +640,9 @@ int caps_dark_loss(const float* v, const float* y, float scale, float* loss, flo
     if (!v || !y || !loss || B < 0 || G <= 0 || Y < 5) return fail(CAPS_E_BADARG, "caps_dark_loss: bad argument (Y >= 5)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long n = (long)B * G;
-    const int blocks = scratch ? (int)std::min<long>(std::max<long>(cdiv(n, 256), 1), CAPS_MARGIN_SCRATCH_FLOATS) : 1;
-    { LaunchScope ls_(kcLoss, st); k_dark_loss<<<blocks, 256, 0, st>>>(v, y, scale, loss, scratch, grad_v, B, G, Y); }
+    const int blocks = (scratch && n > 4096) ? (int)std::min<long>(std::max<long>(cdiv(n, 256), 1), CAPS_MARGIN_SCRATCH_FLOATS) : 1;
+    const int threads = n <= 4096 ? 1024 : 256;            // one block, one launch for the reference's batch (32 x 49 cells)
+    { LaunchScope ls_(kcLoss, st); k_dark_loss<<<blocks, threads, 0, st>>>(v, y, scale, loss, scratch, grad_v, B, G, Y); }
     LAUNCH_CHECK();
     if (blocks > 1) {
         { LaunchScope ls_(kcLoss, st); k_margin_loss_final<<<1, 256, 0, st>>>(scratch, blocks, scale, loss); }

@@ -10,7 +10,7 @@
 // bandwidth).  The general kernels need 9 launches, 32-thread CTAs and the lane-tile re-layout of u for this shape
 // (0.38 ms); the kernels here read u in place.  Two generations (tuning knob "c1v"): the first (below: k_c1_fwd / k_c1_bwd /
 // k_c1_reduce, 0.080 ms per forward + loss + backward step at the DarkCapsuleNet shape) and the second (k_c1_fwd2 /
-// k_c1_bwd2 further down, the default: 0.046 ms, 0.039 ms replayed from a CUDA graph), which the first cross-checks.
+// k_c1_bwd2 further down, the default: 0.042 ms, 0.036 ms replayed from a CUDA graph), which the first cross-checks.
 //   k_c1_fwd     one CTA per group of samples; W (d-major copy, <= 160 KB) staged in shared memory once per CTA;
 //                thread <-> quads of (i,k); fixed-order block reduction; squash in the same kernel
 //   k_c1_bwd     one CTA per 8 samples: ds (+ the margin-loss gradient) in the prologue; thread <-> quads of (i,k) with the

@@ -759,7 +759,7 @@ __global__ void k_reduce_du(const float* __restrict__ du_part, int JG, float* __
 static __global__ void k_margin_loss(const float* __restrict__ v, const int64_t* __restrict__ y, float scale,
                                      float* __restrict__ loss, float* __restrict__ part,
                                      float* __restrict__ scores, int B, int C, int D) {
-    __shared__ float red[256];
+    __shared__ float red[1024];              // blockDim.x <= 1024 (a power of two)
     float acc = 0.f;
     const long n = (long)B * C;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
@@ -785,7 +785,7 @@ static __global__ void k_margin_loss(const float* __restrict__ v, const int64_t*
 }
 
 static __global__ void k_margin_loss_final(const float* __restrict__ part, int n, float scale, float* __restrict__ loss) {
-    __shared__ float red[256];
+    __shared__ float red[1024];              // blockDim.x <= 1024 (a power of two)
     float acc = 0.f;
     for (int e = threadIdx.x; e < n; e += blockDim.x) acc += part[e];
     red[threadIdx.x] = acc;
@@ -808,7 +808,7 @@ static __global__ void k_margin_loss_final(const float* __restrict__ part, int n
 static __global__ void k_dark_loss(const float* __restrict__ v, const float* __restrict__ y, float scale,
                                    float* __restrict__ loss, float* __restrict__ part, float* __restrict__ grad_v,
                                    int B, int G, int Y) {
-    __shared__ float red[256];
+    __shared__ float red[1024];              // blockDim.x <= 1024 (a power of two)
     float acc = 0.f;
     const long n = (long)B * G;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
