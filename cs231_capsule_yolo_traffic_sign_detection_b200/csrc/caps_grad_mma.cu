@@ -28,15 +28,17 @@ namespace caps {
 namespace {
 
 constexpr int kGmIT = 8;          // input capsules per CTA
+constexpr int kGmDuBufs = 3;      // du round buffers: the consumers may run two rounds ahead of the service warp's reduction (2 buffers: 7.66 ms,
+                                  // 3: 7.47, 4: 7.47 at the benchmark shape; the operand ring gets what is left: 7 stages, and 3 would do)
 constexpr int kGmServiceWarps = 1;    // 1: one service warp fills the ring and sums the du fragments; 2: two warps -- measured SLOWER (9.3 vs 7.5 ms): ptxas budgets registers for 16 warps then (128 instead of 154)
 constexpr bool g_use_ffma2 = true;   // G build as 8 packed FMAs per term (scalar-broadcast coefficient) instead of 16 FFMA
 // Consumer warps (= output capsules) per CTA: 8 or 11.  11 + the producer warp = 384 threads is the most that still
 // leaves 168 registers per thread (X^m alone takes 16 M); three warps per scheduler instead of two hide more of the
 // LDS -> split -> HMMA chain, and C = 43 is 4 x 11 - 1.
-__host__ __device__ constexpr int gm_dub(int) { return 2; }          // input capsules per du reduction round (double-buffered)
+__host__ __device__ constexpr int gm_dub(int) { return 2; }          // input capsules per du reduction round (kGmDuBufs round buffers)
 __host__ __device__ constexpr int gm_stage_floats(int M, int JW) { return 272 + (M - 1) * JW * 32; }
 __host__ __device__ constexpr int gm_fixed_floats(int JW) {
-    return kGmIT * JW * 128 /* Wfrag */ + kGmIT * JW * 128 /* dWsm */ + JW * 32 * 16 /* Gs */ + 2 * JW * gm_dub(JW) * 256 /* dusm */;
+    return kGmIT * JW * 128 /* Wfrag */ + kGmIT * JW * 128 /* dWsm */ + JW * 32 * 16 /* Gs */ + kGmDuBufs * JW * gm_dub(JW) * 256 /* dusm */;
 }
 // operand ring depth (units in flight per CTA): what fits next to the fixed tiles, at most 8
 __host__ __device__ constexpr int gm_stages(int M, int JW) {
@@ -148,10 +150,10 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
     float* dWsm = Wfrag + IT * JW * 128;                   // [IT][JW][32 lanes][4]
     float* Gs = dWsm + IT * JW * 128;                      // [JW][32][16] swizzled
     float* dusm = Gs + JW * 32 * 16;                       // [buf 2][JW][DUB][half 2][32 lanes][4]
-    float* ring = dusm + 2 * JW * DUB * 256;                   // [NS][ u tile [kq 2][32][4], halves kGmUSkew apart | coef rows [M-1][JW][32] ]
+    float* ring = dusm + kGmDuBufs * JW * DUB * 256;                   // [NS][ u tile [kq 2][32][4], halves kGmUSkew apart | coef rows [M-1][JW][32] ]
     const uint32_t bars = smem_u32(ring + NS * SF);        // full[NS], empty[NS]
     const uint32_t bar_full = bars, bar_empty = bars + 8 * NS;
-    const uint32_t bar_dufull = bars + 16 * NS, bar_dufree = bar_dufull + 16;      // [2] each: du round buffers
+    const uint32_t bar_dufull = bars + 16 * NS, bar_dufree = bar_dufull + 8 * kGmDuBufs;      // [kGmDuBufs] each: du round buffers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;                 // mma fragment coordinates
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
     for (int e = threadIdx.x; e < IT * JW * 128; e += blockDim.x) dWsm[e] = 0.f;
     if (threadIdx.x == 0) {
         for (int q = 0; q < NS; ++q) { mbar_init(bar_full + 8 * q, 1); mbar_init(bar_empty + 8 * q, JW); }
-        for (int q = 0; q < 2; ++q) { mbar_init(bar_dufull + 8 * q, JW); mbar_init(bar_dufree + 8 * q, 1); }
+        for (int q = 0; q < kGmDuBufs; ++q) { mbar_init(bar_dufull + 8 * q, JW); mbar_init(bar_dufree + 8 * q, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -233,9 +235,9 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
                 if (++fil == ni) { fil = 0; ++ftile; }
                 continue;
             }
-            if (rr < rounds && mbar_test(bar_dufull + 8 * (rr & 1), (rr >> 1) & 1)) {
+            if (rr < rounds && mbar_test(bar_dufull + 8 * (rr % kGmDuBufs), (rr / kGmDuBufs) & 1)) {
                 const int tile = rr / (IT / DUB), ib = (rr % (IT / DUB)) * DUB;
-                const float* dbuf = dusm + (size_t)(rr & 1) * JW * DUB * 256;
+                const float* dbuf = dusm + (size_t)(rr % kGmDuBufs) * JW * DUB * 256;
 #pragma unroll
                 for (int e = 0; e < DUB * 2; ++e) {         // lane <-> fragment lane; e = (ii, half)
                     const int half = e & 1, ii = e >> 1, il = ib + ii;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_dufree + 8 * (rr & 1));
+                if (lane == 0) mbar_arrive(bar_dufree + 8 * (rr % kGmDuBufs));
                 ++rr;
                 continue;
             }
@@ -300,9 +302,9 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
     if (jvalid) load_x(0);
     for (int tile = 0; tile < p.nbt; ++tile) {
         for (int ib = 0; ib < IT; ib += DUB, ++rnd) {
-            // this round's du buffer must have been drained by the service warp (two rounds ago)
-            mbar_wait(bar_dufree + 8 * (rnd & 1), ((rnd >> 1) & 1) ^ 1);
-            float* dbuf = dusm + (size_t)(rnd & 1) * JW * DUB * 256;
+            // this round's du buffer must have been drained by the service warp (kGmDuBufs rounds ago)
+            mbar_wait(bar_dufree + 8 * (rnd % kGmDuBufs), ((rnd / kGmDuBufs) & 1) ^ 1);
+            float* dbuf = dusm + (size_t)(rnd % kGmDuBufs) * JW * DUB * 256;
 #pragma unroll 1
             for (int ii = 0; ii < DUB; ++ii) {
                 const int il = ib + ii;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
                 st4(ds + 128, make_float4(du1[0], du1[1], du1[2], du1[3]));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_dufull + 8 * (rnd & 1));        // release: this warp's fragments are visible
+            if (lane == 0) mbar_arrive(bar_dufull + 8 * (rnd % kGmDuBufs));        // release: this warp's fragments are visible
         }
     }
 
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(32 * JW + 32 * kGmServiceWarps, 1) k_grad_mma(
 template <int M, int JW>
 int launch_t(const Plan& pl, const GradParams& gp, cudaStream_t st) {
     const size_t smem = ((size_t)gm_fixed_floats(JW) + (size_t)gm_stages(M, JW) * gm_stage_floats(M, JW)) * sizeof(float) +
-                        16 * gm_stages(M, JW) + 32;
+                        16 * gm_stages(M, JW) + 16 * kGmDuBufs + 16;
     auto kern = pl.D == 16 ? k_grad_mma<M, JW, false> : k_grad_mma<M, JW, true>;
     if (pl.D == 16) CAPS_SET_SMEM(kern, smem); else CAPS_SET_SMEM(kern, smem);      // one cache per instantiation (and per device)
     dim3 grid(cdiv(pl.N, kGmIT), cdiv(pl.C * cdiv(pl.DP, 16), JW)), block(32 * JW + 32 * kGmServiceWarps);
