@@ -127,3 +127,29 @@ def test_shuffle_follows_numpy_global_rng():
     np.random.seed(3)
     got = runner.train(x, y, m2, torch.optim.SGD(m2.parameters(), lr=0.1), loss_fn, metric, params)
     assert got == want
+
+
+def test_other_input_dtypes_and_float_targets():
+    """uint8 / float64 images go through main.py:57's `.float()`; float targets (the darkcapsule label grid) pass through
+    unchanged; params.device may be a torch.device."""
+    rng = np.random.RandomState(2)
+    params = types.SimpleNamespace(device=torch.device('cpu'), batch_size=4, model='darkcapsule', recon=False, recon_coef=0.0)
+    y = rng.uniform(0, 1, (10, 5)).astype(np.float32)
+    mse = lambda y_hat, yy, p: ((y_hat - yy) ** 2).mean()
+    for x in (rng.randint(0, 255, (10, 8, 8, 3)).astype(np.uint8), rng.uniform(-1, 1, (10, 8, 8, 3))):
+        torch.manual_seed(0)
+        m = TinyNet()
+        got = runner.evaluate(x, y, m, mse, lambda a, b, p: float(np.abs(a - b).mean()), params)
+        want = reference_evaluate(x, y, m, mse, lambda a, b, p: float(np.abs(a - b).mean()), params)
+        assert got == want
+
+
+def test_graph_flag_is_ignored_on_cpu():
+    x, y = _data(9)
+    params = _params('cnn', False)
+    torch.manual_seed(0)
+    m1 = TinyNet()
+    m2 = copy.deepcopy(m1)
+    a = runner.train(x, y, m1, torch.optim.SGD(m1.parameters(), lr=0.1), loss_fn, metric, params, shuffle=False)
+    b = runner.train(x, y, m2, torch.optim.SGD(m2.parameters(), lr=0.1), loss_fn, metric, params, shuffle=False, graph=True)
+    assert a == b and '_caps_runner_graphs' not in m2.__dict__
